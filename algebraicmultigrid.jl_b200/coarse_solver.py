@@ -1,0 +1,89 @@
+"""Coarse solvers — host-side mirror of ``/root/reference/src/coarse_solver.jl``.
+
+Factorising the coarsest matrix is setup work and stays on the host; what the cycle needs is the
+APPLY ``cs(x, b)`` (``multilevel.jl:180,228``), which the device performs as a dense GEMV with the
+operator returned by ``dense_operator()``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class CoarseSolver:
+    def dense_operator(self):
+        raise NotImplementedError
+
+
+class Pinv(CoarseSolver):
+    """Moore-Penrose pseudo-inverse (``coarse_solver.jl:9-16``)."""
+
+    def __init__(self, A):
+        self.pinvA = np.linalg.pinv(A.todense()) if A.n else np.zeros((0, 0))
+
+    def dense_operator(self):
+        return self.pinvA
+
+    def __repr__(self):
+        return "Pinv"
+
+
+class QRSolver(CoarseSolver):
+    """``qr(A)`` then ``F \\ b`` per column (``coarse_solver.jl:66-81``) — the reference's default
+    (``:84``).  For a nonsingular coarse matrix ``F \\ b == inv(A) b``; the host forms that operator
+    from a dense Householder QR.  For a numerically singular one (SPQR would return a basic
+    solution) the minimum-norm operator ``pinv(A)`` is used instead — documented deviation."""
+
+    def __init__(self, A):
+        a = A.todense()
+        n = a.shape[0]
+        if n == 0:
+            self.op = np.zeros((0, 0))
+            return
+        q, r = np.linalg.qr(a)
+        d = np.abs(np.diag(r))
+        if d.min() <= max(a.shape) * np.finfo(float).eps * d.max():
+            self.op = np.linalg.pinv(a)
+        else:
+            import scipy.linalg as sl
+
+            self.op = sl.solve_triangular(r, q.T)
+
+    def dense_operator(self):
+        return self.op
+
+    def __repr__(self):
+        return "QRSolver"
+
+
+class LinearSolveWrapperInternal(CoarseSolver):
+    def __init__(self, A, alg):
+        import scipy.sparse.linalg as spl
+
+        self.alg = alg
+        lu = spl.splu(A.to_scipy().tocsc())
+        self.op = lu.solve(np.eye(A.n)) if A.n else np.zeros((0, 0))
+
+    def dense_operator(self):
+        return self.op
+
+    def __repr__(self):
+        return str(self.alg)
+
+
+class LinearSolveWrapper:
+    """``LinearSolveWrapper(alg)`` (``coarse_solver.jl:50-58``).  LinearSolve.jl does not exist here;
+    ``alg`` is a label (e.g. ``"UMFPACKFactorization"``) and the host uses a sparse LU."""
+
+    def __init__(self, alg="UMFPACKFactorization"):
+        self.alg = alg
+
+    def __call__(self, A):
+        return LinearSolveWrapperInternal(A, self.alg)
+
+
+def UMFPACKFactorization():
+    return "UMFPACKFactorization"
+
+
+def _default_coarse_solver(A):
+    return QRSolver

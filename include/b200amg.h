@@ -1,0 +1,189 @@
+/*
+ * b200amg.h — C-ABI of the B200-native AMG solve-phase engine (libb200amg.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of AlgebraicMultigrid.jl that moves to
+ * the device: the multigrid cycle loop (src/multilevel.jl:152-239) and the relaxations
+ * (src/smoother.jl:1-582), plus the stdlib SpMV / restriction / prolongation / norm calls they
+ * make (call sites src/multilevel.jl:170,188-190,219-220,223,226,233-234), the coarse-solver
+ * APPLY (src/coarse_solver.jl:16,75-81) and the preconditioner entry (src/preconditioner.jl:12-24).
+ * Hierarchy SETUP stays on the host; its result is handed over level by level.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Every function returns an int32 status
+ *     (0 = ok, negative = error); b200amg_last_error() gives a thread-local message.  Nothing
+ *     throws across the boundary.  The Julia shim turns a non-zero status into error(...).
+ *   - matrices arrive exactly as Julia holds them: CSC arrays (colptr, rowval, nzval), fp64
+ *     values, Int64 1-based indices (index_bits = 64, index_base = 1).  0-based and/or int32
+ *     indices are accepted too (what this repo's own host side keeps).  Row indices must be
+ *     sorted inside each column (SparseMatrixCSC invariant).  The arrays are BORROWED for the
+ *     duration of the call only; the library converts to its own device layouts.
+ *   - `adjoint != 0` means the operator is the lazy `Adjoint` of the stored CSC matrix — how the
+ *     reference stores P for Ruge-Stuben (src/classical.jl:64-65) and R for smoothed
+ *     aggregation (src/aggregation.jl:158-159).  m, n are ALWAYS the stored parent's size.
+ *   - vectors: contiguous fp64, length n of the level.  memkind says whether x/b/y pointers are
+ *     host memory (the library does H2D/D2H around the call) or device memory on the handle's GPU.
+ *   - one in-flight call per handle (the reference's workspace is shared mutable state too:
+ *     src/multilevel.jl:176,218-225); distinct handles are independent.  Calls return after the
+ *     result is complete (stream-synchronised).
+ */
+#ifndef B200AMG_H
+#define B200AMG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AMG_VERSION 100
+
+typedef struct b200amg_hierarchy* b200amg_handle_t;
+typedef struct b200amg_smoother_obj* b200amg_smoother_handle_t;
+
+/* status codes */
+enum {
+  B200AMG_OK = 0,
+  B200AMG_ERR_BAD_ARG = -1,
+  B200AMG_ERR_DIM_MISMATCH = -2,      /* Julia: DimensionMismatch */
+  B200AMG_ERR_SINGULAR = -3,          /* Julia: SingularException (NoSymmetry GS/SOR setup, smoother.jl:239-241) */
+  B200AMG_ERR_CUDA = -4,
+  B200AMG_ERR_NCCL = -5,
+  B200AMG_ERR_OOM = -6,
+  B200AMG_ERR_STATE = -7,             /* call order violated (e.g. solve before finalize) */
+  B200AMG_ERR_UNSUPPORTED = -8,
+  B200AMG_ERR_NO_DEVICE = -9          /* no CUDA device: there is NO CPU fallback */
+};
+
+/* smoother kinds — src/smoother.jl:18-23 (GaussSeidel), :92-99 (Jacobi), :173-180 (SOR) */
+enum { B200AMG_SMOOTHER_NONE = 0, B200AMG_SMOOTHER_GS = 1, B200AMG_SMOOTHER_JACOBI = 2, B200AMG_SMOOTHER_SOR = 3 };
+/* sweeps — src/smoother.jl:11-17 */
+enum { B200AMG_SWEEP_FORWARD = 1, B200AMG_SWEEP_BACKWARD = 2, B200AMG_SWEEP_SYMMETRIC = 3 };
+/* symmetry tags — src/utils.jl:1-5.  HERMITIAN selects the "fast" column-as-row smoothers,
+ * NONE the true-A variants (smoother.jl:144-171, :226-582). */
+enum { B200AMG_SYMMETRY_HERMITIAN = 0, B200AMG_SYMMETRY_NONE = 1 };
+/* cycles — src/multilevel.jl:116-124, :200-212 */
+enum { B200AMG_CYCLE_V = 0, B200AMG_CYCLE_W = 1, B200AMG_CYCLE_F = 2 };
+enum { B200AMG_MEM_HOST = 0, B200AMG_MEM_DEVICE = 1 };
+enum { B200AMG_OP_A = 0, B200AMG_OP_P = 1, B200AMG_OP_R = 2 };
+enum { B200AMG_PRE = 0, B200AMG_POST = 1 };
+
+/* A SparseMatrixCSC (optionally wrapped in a lazy Adjoint). */
+typedef struct {
+  int64_t m, n;            /* size of the STORED matrix */
+  const void* colptr;      /* n+1 entries */
+  const void* rowval;      /* nnz entries, sorted per column */
+  const double* nzval;     /* nnz entries */
+  int32_t index_bits;      /* 32 or 64 */
+  int32_t index_base;      /* 0 or 1 */
+  int32_t adjoint;         /* 1: operator = stored' */
+  int32_t reserved;
+} b200amg_csc_t;
+
+/* A smoother configuration: GaussSeidel(sweep; iter) / Jacobi(ω; iter) / SOR(ω, sweep; iter). */
+typedef struct {
+  int32_t kind;
+  int32_t sweep;
+  int32_t iter;
+  int32_t reserved;
+  double omega;
+} b200amg_smoother_t;
+
+const char* b200amg_last_error(void);
+int32_t b200amg_version(void);
+/* number of CUDA devices visible (0 => every compute entry point returns B200AMG_ERR_NO_DEVICE) */
+int32_t b200amg_device_count(void);
+
+/* ---- hierarchy lifecycle : replaces the MultiLevel / Level / MultiLevelWorkspace objects
+ *      (src/multilevel.jl:1-59) as the thing the cycle runs on ------------------------------- */
+int32_t b200amg_create(b200amg_handle_t* out, int32_t device);
+/* push!(levels, Level(A, P, R, pre, post))  — src/classical.jl:48-52, src/aggregation.jl:147-151.
+ * A: n x n.  P: n x nc operator, R: nc x n operator (either may be given as adjoint of the other's
+ * storage, or both as plain CSC as test/gmg.jl:40-46 does). */
+int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200amg_csc_t* P,
+                          const b200amg_csc_t* R, const b200amg_smoother_t* pre,
+                          const b200amg_smoother_t* post, int32_t symmetry);
+/* final_A + coarse solver (src/multilevel.jl:16-17).  The factorisation is setup work and
+ * stays on the host: the caller passes the dense n x n matrix M (column-major) whose product
+ * M*b is the coarse solve — pinv(A) for Pinv (src/coarse_solver.jl:9-16), A^-1 for the
+ * QR/LU solvers (:66-81).  final_A is used when the hierarchy has no levels (multilevel.jl:167). */
+int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n,
+                           const double* coarse_inverse_colmajor);
+/* Optional, before finalize: make this handle one rank of a row-partitioned fine level.
+ * nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host. */
+int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_size,
+                              const void* nccl_unique_id, int64_t id_bytes);
+/* builds device layouts (row-major operators, transposes, wavefront schedules), workspaces and
+ * the captured cycle graphs. */
+int32_t b200amg_finalize(b200amg_handle_t h);
+int32_t b200amg_destroy(b200amg_handle_t h);
+
+/* ---- the solve phase ----------------------------------------------------------------------- */
+/* _solve!(x, ml, b, cycle; maxiter, abstol, reltol, log, calculate_residual)
+ * src/multilevel.jl:158-198.  x: in = initial guess, out = solution.  residuals (may be NULL):
+ * caller-allocated, cap entries; receives ||b|| then one ||b - A x|| per iteration (the `log`
+ * history); *nres = entries written.  *iters = cycles executed. */
+int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cycle,
+                      int32_t maxiter, double abstol, double reltol, int32_t calculate_residual,
+                      double* residuals, int32_t cap, int32_t* nres, int32_t* iters,
+                      int32_t memkind);
+/* __solve!(x, ml, cycle, b, 1): exactly one cycle on the caller's x (src/multilevel.jl:214-239). */
+int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t memkind);
+/* ldiv!(x, p::Preconditioner, b): x .= 0 (init_zero) or x .= b, then one cycle, no residual
+ * (src/preconditioner.jl:12-19). */
+int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t cycle,
+                        int32_t init_zero, int32_t memkind);
+/* smooth!(x, levels[level].presmoother|postsmoother, b)  — src/multilevel.jl:216,236. level is 0-based. */
+int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double* x, const double* b,
+                       int32_t memkind);
+/* mul!(y, levels[level].{A|P|R}, x)  — src/multilevel.jl:219,223,233; src/preconditioner.jl:20.
+ * level == number of levels addresses final_A (op A only). */
+int32_t b200amg_apply(b200amg_handle_t h, int32_t level, int32_t op, double* y, const double* x,
+                      int32_t memkind);
+/* res = b - A_level x  — src/multilevel.jl:188-189, :219-220 fused */
+int32_t b200amg_residual(b200amg_handle_t h, int32_t level, double* r, const double* b,
+                         const double* x, int32_t memkind);
+/* coarse_solver(x, b)  — src/multilevel.jl:180,228 */
+int32_t b200amg_coarse_solve(b200amg_handle_t h, double* x, const double* b, int32_t memkind);
+/* norm(v) over a level-sized vector — src/multilevel.jl:170,190 */
+int32_t b200amg_norm(b200amg_handle_t h, int64_t n, const double* v, double* out, int32_t memkind);
+
+/* Preconditioned CG that stays on the device (the caller of ldiv! in the reference's tests is
+ * IterativeSolvers.cg: test/cycle_tests.jl:25, test/runtests.jl:186,204).  Left-preconditioned
+ * CG on A_1 with one `cycle` per iteration as the preconditioner; stops when
+ * ||r|| <= max(reltol*||r0||, abstol) or after maxiter iterations.  residuals as in solve. */
+int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t maxiter,
+                    double abstol, double reltol, double* residuals, int32_t cap, int32_t* nres,
+                    int32_t* iters, int32_t memkind);
+
+/* ---- standalone smoother objects: setup_smoother(config, A, symmetry) / smooth!(x, s, b)
+ *      (src/smoother.jl:1-10,25-49) ---------------------------------------------------------- */
+int32_t b200amg_smoother_create(b200amg_smoother_handle_t* out, int32_t device, const b200amg_csc_t* A,
+                                const b200amg_smoother_t* config, int32_t symmetry);
+int32_t b200amg_smoother_apply(b200amg_smoother_handle_t s, double* x, const double* b, int32_t memkind);
+int32_t b200amg_smoother_destroy(b200amg_smoother_handle_t s);
+
+/* ---- introspection / measurement ----------------------------------------------------------- */
+int32_t b200amg_num_levels(b200amg_handle_t h);  /* length(ml) = levels + 1 */
+/* level 0..length-1: rows, nnz of A_level; nnz of P (0 for the last); number of forward
+ * wavefronts of its Gauss-Seidel schedule (0 if not built). */
+int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_t* nnz_a,
+                           int64_t* nnz_p, int64_t* wavefronts);
+/* kernels launched by this handle since creation (graph replays count their kernel nodes). */
+int64_t b200amg_launch_count(b200amg_handle_t h);
+/* Time `reps` back-to-back launches of one hot-path kernel on the handle's stream with CUDA
+ * events; returns the average milliseconds per launch in *ms.  what: 0 spmv y=A x, 1 residual,
+ * 2 pre-smoother, 3 restriction, 4 prolongation+correction, 5 one full cycle, 6 norm. */
+int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int32_t cycle, int32_t reps,
+                            int32_t flush_l2, double* ms);
+/* The six phases the reference times with @timeit_debug (src/multilevel.jl:216-236):
+ * 0 Presmoother, 1 Residual eval, 2 Restriction, 3 Coarse solve, 4 Prolongation, 5 Postsmoother.
+ * Runs one un-captured cycle with an event pair around every phase; ms[level*6 + phase]
+ * accumulates (cap >= 6*length). */
+int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int32_t cap);
+/* raw device pointers of the level-0 work vectors (x, b) for zero-copy callers (torch / CUDA.jl) */
+int32_t b200amg_device_vectors(b200amg_handle_t h, double** x, double** b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AMG_H */
