@@ -1,0 +1,325 @@
+"""ctypes binding of ``libb200amg.so`` — the C-ABI in ``include/b200amg.h``.
+
+This is the only route from the host mirror to the solve phase.  If the CUDA library is missing,
+or no GPU is visible, the constructors raise: there is deliberately no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "_lib", "libb200amg.so")
+_lib = None
+
+KIND = {"none": 0, "gs": 1, "jacobi": 2, "sor": 3}
+SWEEP = {"forward": 1, "backward": 2, "symmetric": 3}
+SYMMETRY = {"hermitian": 0, "none": 1}
+MEM_HOST, MEM_DEVICE = 0, 1
+OP_A, OP_P, OP_R = 0, 1, 2
+
+# every symbol include/b200amg.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "b200amg_last_error", "b200amg_version", "b200amg_device_count", "b200amg_create", "b200amg_add_level",
+    "b200amg_set_coarse", "b200amg_set_partition", "b200amg_finalize", "b200amg_destroy", "b200amg_solve",
+    "b200amg_cycle", "b200amg_precond", "b200amg_smooth", "b200amg_apply", "b200amg_residual",
+    "b200amg_coarse_solve", "b200amg_norm", "b200amg_pcg", "b200amg_smoother_create", "b200amg_smoother_apply",
+    "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
+    "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors",
+]
+
+
+class CscDesc(C.Structure):
+    """``b200amg_csc_t``"""
+
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("colptr", C.c_void_p), ("rowval", C.c_void_p),
+                ("nzval", C.c_void_p), ("index_bits", C.c_int32), ("index_base", C.c_int32),
+                ("adjoint", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SmootherDesc(C.Structure):
+    """``b200amg_smoother_t``"""
+
+    _fields_ = [("kind", C.c_int32), ("sweep", C.c_int32), ("iter", C.c_int32), ("reserved", C.c_int32),
+                ("omega", C.c_double)]
+
+
+class B200AmgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200amg error {code}: {msg}")
+        self.code = code
+
+
+def build(force: bool = False) -> None:
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcdir = os.path.join(_HERE, "csrc", "device")
+    srcs = [os.path.join(srcdir, f) for f in os.listdir(srcdir)] + [os.path.join(_HERE, "..", "include", "b200amg.h")]
+    stale = (not os.path.exists(_LIBPATH)) or any(os.path.getmtime(s) > os.path.getmtime(_LIBPATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc"), "device"], stdout=subprocess.DEVNULL)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise B200AmgError(-9, f"{_LIBPATH} is missing: build it with __graft_entry__.build() "
+                                   "(the solve phase has no CPU fallback)")
+        L = C.CDLL(_LIBPATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        pcsc, psm = C.POINTER(CscDesc), C.POINTER(SmootherDesc)
+        L.b200amg_last_error.restype = C.c_char_p
+        L.b200amg_version.restype = i32
+        L.b200amg_device_count.restype = i32
+        sigs = {
+            "b200amg_create": [C.POINTER(vp), i32],
+            "b200amg_add_level": [vp, pcsc, pcsc, pcsc, psm, psm, i32],
+            "b200amg_set_coarse": [vp, pcsc, i64, vp],
+            "b200amg_set_partition": [vp, i32, i32, vp, i64],
+            "b200amg_finalize": [vp],
+            "b200amg_destroy": [vp],
+            "b200amg_solve": [vp, vp, vp, i32, i32, dbl, dbl, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), i32],
+            "b200amg_cycle": [vp, vp, vp, i32, i32],
+            "b200amg_precond": [vp, vp, vp, i32, i32, i32],
+            "b200amg_smooth": [vp, i32, i32, vp, vp, i32],
+            "b200amg_apply": [vp, i32, i32, vp, vp, i32],
+            "b200amg_residual": [vp, i32, vp, vp, vp, i32],
+            "b200amg_coarse_solve": [vp, vp, vp, i32],
+            "b200amg_norm": [vp, i64, vp, C.POINTER(dbl), i32],
+            "b200amg_pcg": [vp, vp, vp, i32, i32, dbl, dbl, vp, i32, C.POINTER(i32), C.POINTER(i32), i32],
+            "b200amg_smoother_create": [C.POINTER(vp), i32, pcsc, psm, i32],
+            "b200amg_smoother_apply": [vp, vp, vp, i32],
+            "b200amg_smoother_destroy": [vp],
+            "b200amg_num_levels": [vp],
+            "b200amg_level_info": [vp, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
+            "b200amg_time_kernel": [vp, i32, i32, i32, i32, i32, C.POINTER(dbl)],
+            "b200amg_profile_cycle": [vp, i32, vp, i32],
+            "b200amg_device_vectors": [vp, C.POINTER(vp), C.POINTER(vp)],
+        }
+        for name, args in sigs.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = i32
+        L.b200amg_launch_count.argtypes = [vp]
+        L.b200amg_launch_count.restype = i64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200AmgError(rc, lib().b200amg_last_error().decode(errors="replace"))
+
+
+def device_count() -> int:
+    return int(lib().b200amg_device_count())
+
+
+def _ptr(a):
+    """Pointer of a numpy array (host) or a raw integer device pointer / object with data_ptr()."""
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+def _memkind(a):
+    if isinstance(a, np.ndarray):
+        return MEM_HOST
+    if hasattr(a, "is_cuda"):
+        if not a.is_cuda:
+            raise TypeError("torch tensors passed to the engine must live on the GPU (or pass numpy arrays)")
+        return MEM_DEVICE
+    return MEM_DEVICE
+
+
+def csc_desc(op, keep):
+    """``b200amg_csc_t`` for a ``SparseMatrixCSC`` or a lazy ``Adjoint`` of one."""
+    adj = 0
+    if hasattr(op, "parent"):
+        op, adj = op.parent, 1
+    keep.append(op)
+    d = CscDesc()
+    d.m, d.n = op.m, op.n
+    d.colptr, d.rowval, d.nzval = op.colptr.ctypes.data, op.rowval.ctypes.data, op.nzval.ctypes.data
+    d.index_bits = op.colptr.dtype.itemsize * 8
+    d.index_base = 0
+    d.adjoint = adj
+    return d
+
+
+def smoother_desc(config):
+    d = SmootherDesc()
+    if config is None:
+        d.kind = 0
+        return d
+    d.kind = KIND[config.kind]
+    d.sweep = SWEEP[getattr(config, "sweep_name", "symmetric")]
+    d.iter = int(config.iter)
+    d.omega = float(getattr(config, "omega", 1.0))
+    return d
+
+
+def _default_device():
+    if "B200AMG_DEVICE" in os.environ:
+        return int(os.environ["B200AMG_DEVICE"])
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    return 0
+
+
+class DeviceHierarchy:
+    """Device-resident hierarchy: the handle behind a host ``MultiLevel``."""
+
+    def __init__(self, ml, device=None, partition=None):
+        L = lib()
+        self._h = C.c_void_p()
+        self.device = _default_device() if device is None else device
+        _check(L.b200amg_create(C.byref(self._h), self.device))
+        keep = []
+        try:
+            if partition is not None:
+                rank, world, uid = partition
+                buf = (C.c_char * len(uid)).from_buffer_copy(uid)
+                _check(L.b200amg_set_partition(self._h, rank, world, C.cast(buf, C.c_void_p), len(uid)))
+            for lv in ml.levels:
+                a, p, r = csc_desc(lv.A, keep), csc_desc(lv.P, keep), csc_desc(lv.R, keep)
+                pre, post = smoother_desc(lv.presmoother.config), smoother_desc(lv.postsmoother.config)
+                sym = SYMMETRY[lv.presmoother.symmetry_name]
+                _check(L.b200amg_add_level(self._h, C.byref(a), C.byref(p), C.byref(r), C.byref(pre), C.byref(post), sym))
+            fa = csc_desc(ml.final_A, keep)
+            inv = np.ascontiguousarray(np.asarray(ml.coarse_solver.dense_operator(), dtype=np.float64).reshape(-1, order="F"))
+            _check(L.b200amg_set_coarse(self._h, C.byref(fa), ml.final_A.n, _ptr(inv)))
+            _check(L.b200amg_finalize(self._h))
+        except Exception:
+            L.b200amg_destroy(self._h)
+            self._h = None
+            raise
+        self.n = ml.levels[0].A.n if ml.levels else ml.final_A.n
+        self.nlevels = len(ml.levels) + 1
+
+    def close(self):
+        if self._h:
+            lib().b200amg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- solve phase -----------------------------------------------------------------------
+    def solve(self, x, b, cycle=0, maxiter=100, abstol=0.0, reltol=1.4901161193847656e-08, calculate_residual=True):
+        cap = int(maxiter) + 2
+        res = np.zeros(cap)
+        nres, iters = C.c_int32(0), C.c_int32(0)
+        _check(lib().b200amg_solve(self._h, _ptr(x), _ptr(b), cycle, maxiter, abstol, reltol, int(calculate_residual),
+                                   _ptr(res), cap, C.byref(nres), C.byref(iters), _memkind(x)))
+        return res[: nres.value].copy(), iters.value
+
+    def cycle(self, x, b, cycle=0):
+        _check(lib().b200amg_cycle(self._h, _ptr(x), _ptr(b), cycle, _memkind(x)))
+        return x
+
+    def precond(self, x, b, cycle=0, init_zero=True):
+        _check(lib().b200amg_precond(self._h, _ptr(x), _ptr(b), cycle, int(init_zero), _memkind(x)))
+        return x
+
+    def smooth(self, level, which, x, b):
+        _check(lib().b200amg_smooth(self._h, level, which, _ptr(x), _ptr(b), _memkind(x)))
+        return x
+
+    def apply(self, level, op, y, x):
+        _check(lib().b200amg_apply(self._h, level, op, _ptr(y), _ptr(x), _memkind(x)))
+        return y
+
+    def residual(self, level, r, b, x):
+        _check(lib().b200amg_residual(self._h, level, _ptr(r), _ptr(b), _ptr(x), _memkind(x)))
+        return r
+
+    def coarse_solve(self, x, b):
+        _check(lib().b200amg_coarse_solve(self._h, _ptr(x), _ptr(b), _memkind(x)))
+        return x
+
+    def norm(self, v, n=None):
+        out = C.c_double(0)
+        n = int(v.size if n is None and isinstance(v, np.ndarray) else (n if n is not None else v.numel()))
+        _check(lib().b200amg_norm(self._h, n, _ptr(v), C.byref(out), _memkind(v)))
+        return out.value
+
+    def pcg(self, x, b, cycle=0, maxiter=None, abstol=0.0, reltol=1.4901161193847656e-08):
+        maxiter = self.n if maxiter is None else int(maxiter)
+        cap = maxiter + 2
+        res = np.zeros(cap)
+        nres, iters = C.c_int32(0), C.c_int32(0)
+        _check(lib().b200amg_pcg(self._h, _ptr(x), _ptr(b), cycle, maxiter, abstol, reltol, _ptr(res), cap,
+                                 C.byref(nres), C.byref(iters), _memkind(x)))
+        return res[: nres.value].copy(), iters.value
+
+    # -- introspection / measurement -----------------------------------------------------------
+    def level_info(self, level):
+        n, nnza, nnzp, wf = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().b200amg_level_info(self._h, level, C.byref(n), C.byref(nnza), C.byref(nnzp), C.byref(wf)))
+        return {"n": n.value, "nnz_a": nnza.value, "nnz_p": nnzp.value, "wavefronts": wf.value}
+
+    def launch_count(self):
+        return int(lib().b200amg_launch_count(self._h))
+
+    def time_kernel(self, level, what, cycle=0, reps=20, flush_l2=False):
+        ms = C.c_double(0)
+        _check(lib().b200amg_time_kernel(self._h, level, what, cycle, reps, int(flush_l2), C.byref(ms)))
+        return ms.value
+
+    def profile_cycle(self, cycle=0):
+        cap = 6 * self.nlevels
+        ms = np.zeros(cap)
+        _check(lib().b200amg_profile_cycle(self._h, cycle, _ptr(ms), cap))
+        return ms.reshape(self.nlevels, 6)
+
+    def device_vectors(self):
+        x, b = C.c_void_p(), C.c_void_p()
+        _check(lib().b200amg_device_vectors(self._h, C.byref(x), C.byref(b)))
+        return x.value, b.value
+
+
+class DeviceSmoother:
+    """Device-side cache of a standalone smoother (``setup_smoother`` / ``smooth!``)."""
+
+    def __init__(self, A, config, symmetry_name, device=None):
+        L = lib()
+        self._s = C.c_void_p()
+        keep = []
+        a = csc_desc(A, keep)
+        cfg = smoother_desc(config)
+        rc = L.b200amg_smoother_create(C.byref(self._s), _default_device() if device is None else device, C.byref(a),
+                                       C.byref(cfg), SYMMETRY[symmetry_name])
+        if rc == -3:
+            from .smoother import SingularException
+
+            msg = L.b200amg_last_error().decode()
+            raise SingularException(int(msg[msg.index("(") + 1: msg.index(")")]))
+        _check(rc)
+
+    def apply(self, x, b):
+        xd = x if not isinstance(x, np.ndarray) else np.ascontiguousarray(x, dtype=np.float64)
+        bd = b if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, dtype=np.float64)
+        _check(lib().b200amg_smoother_apply(self._s, _ptr(xd), _ptr(bd), _memkind(xd)))
+        if isinstance(x, np.ndarray) and xd is not x:
+            x[...] = xd
+        return x
+
+    def close(self):
+        if self._s:
+            lib().b200amg_smoother_destroy(self._s)
+            self._s = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

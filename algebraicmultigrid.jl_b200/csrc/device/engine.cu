@@ -1,0 +1,1131 @@
+// libb200amg.so — the C-ABI device engine declared in include/b200amg.h.
+//
+// Owns device copies of every level of an AMG hierarchy and runs the whole solve phase of
+// AlgebraicMultigrid.jl (src/multilevel.jl:152-239, src/smoother.jl, src/preconditioner.jl:12-24)
+// on one B200: the cycle is a static sequence of kernels captured once per cycle type into a
+// CUDA graph and replayed per iteration.  There is no CPU fallback: without a device every
+// compute entry point fails with B200AMG_ERR_NO_DEVICE.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "b200amg.h"
+#include "kernels.cuh"
+
+using namespace b200amg;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int32_t fail(int32_t code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+struct AmgError {
+  int32_t code;
+  std::string msg;
+};
+#define CUDA_OK(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      char _b[512];                                                                                \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw AmgError{_e == cudaErrorMemoryAllocation ? B200AMG_ERR_OOM : B200AMG_ERR_CUDA, _b};    \
+    }                                                                                              \
+  } while (0)
+#define REQUIRE(cond, code, ...)                                     \
+  do {                                                               \
+    if (!(cond)) {                                                   \
+      char _b[512];                                                  \
+      snprintf(_b, sizeof _b, __VA_ARGS__);                          \
+      throw AmgError{code, _b};                                      \
+    }                                                                \
+  } while (0)
+#define API_BEGIN try {
+#define API_END                                         \
+  }                                                     \
+  catch (const AmgError& e) {                           \
+    return fail(e.code, "%s", e.msg.c_str());           \
+  }                                                     \
+  catch (const std::bad_alloc&) {                       \
+    return fail(B200AMG_ERR_OOM, "host out of memory"); \
+  }                                                     \
+  catch (const std::exception& e) {                     \
+    return fail(B200AMG_ERR_BAD_ARG, "%s", e.what());   \
+  }                                                     \
+  return B200AMG_OK;
+
+// ------------------------------------------------------------------------------------------
+// host-side sparse staging (int32, 0-based, "by rows" = compressed along the first index)
+// ------------------------------------------------------------------------------------------
+struct HostCsr {
+  int64_t nrows = 0, ncols = 0;
+  std::vector<int> ptr, idx;
+  std::vector<double> val;
+  int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
+};
+
+// The CSC arrays of an m x n matrix ARE the CSR arrays of its n x m transpose.
+static HostCsr stage_csc_as_rows_of_transpose(const b200amg_csc_t* M) {
+  REQUIRE(M && M->colptr && (M->index_bits == 32 || M->index_bits == 64) && (M->index_base == 0 || M->index_base == 1),
+          B200AMG_ERR_BAD_ARG, "bad matrix descriptor (index_bits must be 32/64, index_base 0/1)");
+  REQUIRE(M->m >= 0 && M->n >= 0 && M->m < INT32_MAX && M->n < INT32_MAX, B200AMG_ERR_UNSUPPORTED,
+          "matrix dimension does not fit the int32 device index width");
+  HostCsr out;
+  out.nrows = M->n;
+  out.ncols = M->m;
+  out.ptr.resize(M->n + 1);
+  const int base = M->index_base;
+  int64_t nnz;
+  if (M->index_bits == 64) {
+    const int64_t* cp = (const int64_t*)M->colptr;
+    nnz = cp[M->n] - base;
+    REQUIRE(nnz >= 0 && nnz < INT32_MAX, B200AMG_ERR_UNSUPPORTED, "nnz does not fit the int32 device index width");
+    for (int64_t j = 0; j <= M->n; ++j) out.ptr[j] = (int)(cp[j] - base);
+  } else {
+    const int32_t* cp = (const int32_t*)M->colptr;
+    nnz = cp[M->n] - base;
+    REQUIRE(nnz >= 0, B200AMG_ERR_BAD_ARG, "negative nnz");
+    for (int64_t j = 0; j <= M->n; ++j) out.ptr[j] = cp[j] - base;
+  }
+  REQUIRE(nnz == 0 || (M->rowval && M->nzval), B200AMG_ERR_BAD_ARG, "null rowval/nzval");
+  out.idx.resize(nnz);
+  out.val.assign(M->nzval, M->nzval + nnz);
+  if (M->index_bits == 64) {
+    const int64_t* rv = (const int64_t*)M->rowval;
+    for (int64_t k = 0; k < nnz; ++k) out.idx[k] = (int)(rv[k] - base);
+  } else {
+    const int32_t* rv = (const int32_t*)M->rowval;
+    for (int64_t k = 0; k < nnz; ++k) out.idx[k] = rv[k] - base;
+  }
+  for (int64_t j = 0; j < M->n; ++j) {
+    REQUIRE(out.ptr[j] <= out.ptr[j + 1], B200AMG_ERR_BAD_ARG, "colptr not monotone");
+    for (int k = out.ptr[j]; k < out.ptr[j + 1]; ++k) {
+      REQUIRE(out.idx[k] >= 0 && out.idx[k] < M->m, B200AMG_ERR_BAD_ARG, "row index out of range");
+      REQUIRE(k == out.ptr[j] || out.idx[k - 1] < out.idx[k], B200AMG_ERR_BAD_ARG,
+              "row indices must be sorted and unique inside each column");
+    }
+  }
+  return out;
+}
+
+static HostCsr transpose(const HostCsr& a) {
+  HostCsr t;
+  t.nrows = a.ncols;
+  t.ncols = a.nrows;
+  const int64_t nnz = a.nnz();
+  t.ptr.assign(t.nrows + 1, 0);
+  t.idx.resize(nnz);
+  t.val.resize(nnz);
+  for (int64_t k = 0; k < nnz; ++k) t.ptr[a.idx[k] + 1]++;
+  for (int64_t i = 0; i < t.nrows; ++i) t.ptr[i + 1] += t.ptr[i];
+  std::vector<int> next(t.ptr.begin(), t.ptr.end() - 1);
+  for (int64_t r = 0; r < a.nrows; ++r)
+    for (int k = a.ptr[r]; k < a.ptr[r + 1]; ++k) {
+      const int q = next[a.idx[k]]++;
+      t.idx[q] = (int)r;
+      t.val[q] = a.val[k];
+    }
+  return t;
+}
+
+static bool bit_equal(const HostCsr& a, const HostCsr& b) {
+  return a.nrows == b.nrows && a.ncols == b.ncols && a.ptr == b.ptr && a.idx == b.idx &&
+         std::memcmp(a.val.data(), b.val.data(), sizeof(double) * a.val.size()) == 0;
+}
+
+// operator given as (stored CSC, adjoint flag) -> the operator compressed by ITS rows
+static HostCsr stage_operator_by_rows(const b200amg_csc_t* M) {
+  HostCsr t = stage_csc_as_rows_of_transpose(M);  // rows of stored'
+  if (M->adjoint) return t;                       // operator == stored'
+  return transpose(t);                            // operator == stored
+}
+
+// Wavefront (level) schedule for an in-order sweep over rows 0..n-1 (forward) or n-1..0 (backward)
+// of `a`, honouring both true dependencies (a_ij, j earlier) and anti-dependencies (a_ji): the
+// dependency graph is the symmetrised pattern, which is why `at` (the transpose pattern) is needed.
+struct HostSchedule {
+  std::vector<int> rows;    // rows grouped by wavefront, ascending inside a wavefront
+  std::vector<int> lvlptr;  // nlev + 1
+};
+static HostSchedule build_schedule(const HostCsr& a, const HostCsr& at, bool forward) {
+  const int64_t n = a.nrows;
+  std::vector<int> level(n, 0);
+  int nlev = 0;
+  for (int64_t s = 0; s < n; ++s) {
+    const int64_t i = forward ? s : n - 1 - s;
+    int lv = 0;
+    for (int k = a.ptr[i]; k < a.ptr[i + 1]; ++k) {
+      const int j = a.idx[k];
+      if (forward ? j < i : j > i) lv = std::max(lv, level[j] + 1);
+    }
+    if (&at != &a)
+      for (int k = at.ptr[i]; k < at.ptr[i + 1]; ++k) {
+        const int j = at.idx[k];
+        if (forward ? j < i : j > i) lv = std::max(lv, level[j] + 1);
+      }
+    level[i] = lv;
+    nlev = std::max(nlev, lv + 1);
+  }
+  HostSchedule sc;
+  sc.lvlptr.assign(nlev + 1, 0);
+  for (int64_t i = 0; i < n; ++i) sc.lvlptr[level[i] + 1]++;
+  for (int l = 0; l < nlev; ++l) sc.lvlptr[l + 1] += sc.lvlptr[l];
+  sc.rows.resize(n);
+  std::vector<int> next(sc.lvlptr.begin(), sc.lvlptr.end() - 1);
+  for (int64_t i = 0; i < n; ++i) sc.rows[next[level[i]]++] = (int)i;
+  return sc;
+}
+
+// ------------------------------------------------------------------------------------------
+// device objects
+// ------------------------------------------------------------------------------------------
+template <typename T>
+static T* dev_alloc(int64_t count) {
+  T* p = nullptr;
+  CUDA_OK(cudaMalloc(&p, sizeof(T) * (size_t)std::max<int64_t>(count, 1)));
+  return p;
+}
+template <typename T>
+static T* dev_upload(const std::vector<T>& v, int64_t pad = 0) {
+  T* p = dev_alloc<T>((int64_t)v.size() + pad);
+  if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return p;
+}
+
+struct DevCsr {
+  int64_t nrows = 0, ncols = 0, nnz = 0;
+  int* ptr = nullptr;
+  int* idx = nullptr;
+  double* val = nullptr;
+  int lanes = 8;  // lanes per row of the vector kernels
+  bool owner = false;
+  void upload(const HostCsr& h) {
+    nrows = h.nrows; ncols = h.ncols; nnz = h.nnz();
+    ptr = dev_upload(h.ptr);
+    idx = dev_upload(h.idx, 8);
+    val = dev_upload(h.val, 8);
+    owner = true;
+    const double mean = nrows ? (double)nnz / (double)nrows : 0.0;
+    lanes = 2;
+    while (lanes < 32 && lanes < mean) lanes *= 2;
+  }
+  void alias(const DevCsr& o) { *this = o; owner = false; }
+  void release() {
+    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); }
+    ptr = idx = nullptr; val = nullptr; owner = false;
+  }
+};
+
+struct SweepItem {
+  int lv_begin, lv_end;  // wavefront range
+  bool single_cta;
+};
+struct DevSchedule {
+  int nlev = 0;
+  int64_t n = 0;
+  int* rows = nullptr;
+  int* lvlptr = nullptr;
+  std::vector<int> h_lvlptr;
+  std::vector<SweepItem> items;
+  bool built = false;
+  void upload(const HostSchedule& h, int lanes) {
+    nlev = (int)h.lvlptr.size() - 1;
+    n = (int64_t)h.rows.size();
+    rows = dev_upload(h.rows);
+    lvlptr = dev_upload(h.lvlptr);
+    h_lvlptr = h.lvlptr;
+    // group runs of narrow wavefronts into single-CTA items
+    const int narrow = 4 * (kCtaThreads / lanes);  // <= 4 passes of one CTA
+    int l = 0;
+    while (l < nlev) {
+      const int cnt = h_lvlptr[l + 1] - h_lvlptr[l];
+      if (cnt <= narrow) {
+        int e = l + 1;
+        while (e < nlev && h_lvlptr[e + 1] - h_lvlptr[e] <= narrow) ++e;
+        items.push_back({l, e, true});
+        l = e;
+      } else {
+        items.push_back({l, l + 1, false});
+        ++l;
+      }
+    }
+    built = true;
+  }
+  void release() { cudaFree(rows); cudaFree(lvlptr); rows = lvlptr = nullptr; built = false; }
+};
+
+struct SmootherCfg {
+  int kind = 0, sweep = 3, iter = 1;
+  double omega = 1.0;
+};
+static SmootherCfg to_cfg(const b200amg_smoother_t* s) {
+  SmootherCfg c;
+  if (!s) { c.kind = 0; return c; }
+  REQUIRE(s->kind >= 0 && s->kind <= 3, B200AMG_ERR_BAD_ARG, "unknown smoother kind %d", s->kind);
+  c.kind = s->kind; c.sweep = s->sweep; c.iter = s->iter; c.omega = s->omega;
+  if (c.kind == B200AMG_SMOOTHER_GS || c.kind == B200AMG_SMOOTHER_SOR)
+    REQUIRE(c.sweep >= 1 && c.sweep <= 3, B200AMG_ERR_BAD_ARG, "unknown sweep %d", c.sweep);
+  REQUIRE(c.iter >= 0, B200AMG_ERR_BAD_ARG, "negative iteration count");
+  return c;
+}
+
+// A matrix prepared for relaxation: the rows the smoother walks + wavefront schedules + diagonal.
+struct SmootherMatrix {
+  DevCsr A;      // true A by rows
+  DevCsr At;     // rows of A' (== the reference's CSC columns); aliases A when A is bit-symmetric
+  bool symmetric_bits = false;
+  int symmetry = B200AMG_SYMMETRY_HERMITIAN;
+  DevSchedule fwd, bwd;
+  double* diag = nullptr;   // diagonal of the walked matrix (same for A and A')
+  int64_t n = 0;
+  const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
+
+  // hA_t: rows of A' (the staged CSC); need_gs: build wavefront schedules
+  void build(const HostCsr& hAt, int symmetry_, bool need_fwd, bool need_bwd, bool need_true_A) {
+    symmetry = symmetry_;
+    n = hAt.nrows;
+    HostCsr hA = transpose(hAt);
+    symmetric_bits = bit_equal(hA, hAt);
+    At.upload(hAt);
+    if (symmetric_bits) A.alias(At);
+    else if (need_true_A || symmetry == B200AMG_SYMMETRY_NONE) A.upload(hA);
+    const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt : hA;
+    const HostCsr& wt = symmetric_bits ? w : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA : hAt);
+    std::vector<double> d(n, 0.0);
+    for (int64_t i = 0; i < n; ++i)
+      for (int k = w.ptr[i]; k < w.ptr[i + 1]; ++k)
+        if (w.idx[k] == i) d[i] = w.val[k];
+    diag = dev_upload(d);
+    if (symmetry == B200AMG_SYMMETRY_NONE && (need_fwd || need_bwd)) {
+      // DiagonalIndices(A): SingularException on a missing / zero diagonal  (smoother.jl:233-248)
+      for (int64_t i = 0; i < n; ++i)
+        REQUIRE(d[i] != 0.0, B200AMG_ERR_SINGULAR, "SingularException(%lld)", (long long)(i + 1));
+    }
+    if (need_fwd) fwd.upload(build_schedule(w, wt, true), walked().lanes);
+    if (need_bwd) bwd.upload(build_schedule(w, wt, false), walked().lanes);
+  }
+  void release() {
+    A.release(); At.release(); fwd.release(); bwd.release();
+    cudaFree(diag); diag = nullptr;
+  }
+};
+
+static bool cfg_needs_fwd(const SmootherCfg& c) {
+  return (c.kind == B200AMG_SMOOTHER_GS || c.kind == B200AMG_SMOOTHER_SOR) && (c.sweep == 1 || c.sweep == 3);
+}
+static bool cfg_needs_bwd(const SmootherCfg& c) {
+  return (c.kind == B200AMG_SMOOTHER_GS || c.kind == B200AMG_SMOOTHER_SOR) && (c.sweep == 2 || c.sweep == 3);
+}
+
+struct Level {
+  int64_t n = 0, nc = 0;
+  SmootherMatrix M;
+  DevCsr P, R;
+  SmootherCfg pre, post;
+  double *res = nullptr, *coarse_x = nullptr, *coarse_b = nullptr, *temp = nullptr;
+};
+
+struct b200amg_hierarchy {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<std::unique_ptr<Level>> levels;
+  // coarsest
+  bool have_coarse = false;
+  int64_t nfinal = 0;
+  DevCsr finalA;
+  double* coarse_inv = nullptr;
+  double* res_final = nullptr;
+  // level-0 work vectors
+  int64_t n0 = 0;
+  double *x0 = nullptr, *b0 = nullptr;
+  // reductions
+  double* partial = nullptr;
+  double* scalars = nullptr;  // device scalars: [0] norm, [1] rho, [2] rho_prev, [3] uq, [4] scratch
+  double* h_scalars = nullptr;  // pinned
+  // PCG
+  double *pcg_u = nullptr, *pcg_q = nullptr, *pcg_x = nullptr;
+  // graphs
+  cudaGraphExec_t cycle_graph[3] = {nullptr, nullptr, nullptr};
+  int64_t cycle_graph_launches[3] = {0, 0, 0};
+  cudaGraphExec_t resnorm_graph = nullptr;
+  bool use_graphs = true;
+  bool finalized = false;
+  bool capturing = false;
+  int64_t launches = 0;       // kernels launched (graph replays add their node counts)
+  int64_t capture_count = 0;  // kernels recorded into the graph being captured
+  // L2 flush buffer for time_kernel
+  void* flush = nullptr;
+  size_t flush_bytes = 0;
+  // profiling
+  bool profiling = false;
+  std::vector<double>* prof_ms = nullptr;
+};
+typedef b200amg_hierarchy H;
+
+static inline void count_launch(H* h) {
+  if (h->capturing) h->capture_count++; else h->launches++;
+}
+static inline unsigned grid_for(int64_t work_items) {
+  return (unsigned)std::max<int64_t>(1, (work_items + kThreads - 1) / kThreads);
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+template <int MODE>
+static void launch_csr(H* h, const DevCsr& A, const double* x, const double* b, double* y) {
+  if (A.nrows == 0) return;
+  const unsigned g = grid_for(A.nrows * A.lanes);
+  switch (A.lanes) {
+    case 2: csr_vec_kernel<2, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
+    case 4: csr_vec_kernel<4, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
+    case 8: csr_vec_kernel<8, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
+    case 16: csr_vec_kernel<16, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
+    default: csr_vec_kernel<32, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
+  }
+  count_launch(h);
+}
+static void spmv(H* h, const DevCsr& A, const double* x, double* y) { launch_csr<0>(h, A, x, nullptr, y); }
+static void residual(H* h, const DevCsr& A, const double* x, const double* b, double* r) { launch_csr<1>(h, A, x, b, r); }
+static void spmv_add(H* h, const DevCsr& A, const double* x, double* y) { launch_csr<2>(h, A, x, nullptr, y); }
+
+static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const double* b, double* xout, double w) {
+  const unsigned g = grid_for(A.nrows * A.lanes);
+  switch (A.lanes) {
+    case 2: jacobi_fast_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
+    case 4: jacobi_fast_kernel<4><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
+    case 8: jacobi_fast_kernel<8><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
+    case 16: jacobi_fast_kernel<16><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
+    default: jacobi_fast_kernel<32><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
+  }
+  count_launch(h);
+}
+static void launch_jacobi_general(H* h, const DevCsr& A, const double* diag, const double* xin, const double* b,
+                                  double* xout, double w) {
+  const unsigned g = grid_for(A.nrows * A.lanes);
+  switch (A.lanes) {
+    case 2: jacobi_general_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
+    case 4: jacobi_general_kernel<4><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
+    case 8: jacobi_general_kernel<8><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
+    case 16: jacobi_general_kernel<16><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
+    default: jacobi_general_kernel<32><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
+  }
+  count_launch(h);
+}
+
+template <int T>
+static void launch_sweep_T(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  for (const SweepItem& it : sc.items) {
+    if (it.single_cta) {
+      gs_cta_levels_kernel<T><<<1, kCtaThreads, 0, h->stream>>>(sc.rows, sc.lvlptr, it.lv_begin, it.lv_end, A.ptr, A.idx,
+                                                               A.val, x, b, w, sor);
+    } else {
+      const int s = sc.h_lvlptr[it.lv_begin], cnt = sc.h_lvlptr[it.lv_begin + 1] - s;
+      gs_wavefront_kernel<T><<<grid_for((int64_t)cnt * T), kThreads, 0, h->stream>>>(sc.rows + s, cnt, A.ptr, A.idx, A.val, x,
+                                                                                  b, w, sor);
+    }
+    count_launch(h);
+  }
+}
+static void launch_sweep(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  switch (A.lanes) {
+    case 2: launch_sweep_T<2>(h, A, sc, x, b, w, sor); break;
+    case 4: launch_sweep_T<4>(h, A, sc, x, b, w, sor); break;
+    case 8: launch_sweep_T<8>(h, A, sc, x, b, w, sor); break;
+    case 16: launch_sweep_T<16>(h, A, sc, x, b, w, sor); break;
+    default: launch_sweep_T<32>(h, A, sc, x, b, w, sor); break;
+  }
+}
+
+// smooth!(x, s, b) for one configured smoother on a prepared matrix.  temp: n scratch doubles.
+// x_is_zero: the caller guarantees x == 0 on entry (enables the exact zero-guess Jacobi shortcut).
+static void smooth(H* h, const SmootherMatrix& M, const SmootherCfg& c, double* x, const double* b, double* temp,
+                   bool x_is_zero) {
+  if (c.kind == B200AMG_SMOOTHER_NONE || M.n == 0) return;
+  const DevCsr& A = M.walked();
+  if (c.kind == B200AMG_SMOOTHER_JACOBI) {
+    const bool general = M.symmetry == B200AMG_SYMMETRY_NONE;
+    double* cur = x;
+    double* other = temp;
+    for (int it = 0; it < c.iter; ++it) {
+      if (it == 0 && x_is_zero) {
+        // elementwise: safe in place, no buffer swap
+        jacobi_zero_guess_kernel<<<grid_for(M.n), kThreads, 0, h->stream>>>(M.n, M.diag, b, cur, c.omega, general ? 1 : 0);
+        count_launch(h);
+        continue;
+      } else if (general) {
+        launch_jacobi_general(h, A, M.diag, cur, b, other, c.omega);
+      } else {
+        launch_jacobi_fast(h, A, cur, b, other, c.omega);
+      }
+      std::swap(cur, other);
+    }
+    if (cur != x) CUDA_OK(cudaMemcpyAsync(x, cur, sizeof(double) * M.n, cudaMemcpyDeviceToDevice, h->stream));
+    return;
+  }
+  const int sor = c.kind == B200AMG_SMOOTHER_SOR;
+  for (int it = 0; it < c.iter; ++it) {
+    if (c.sweep == 1 || c.sweep == 3) launch_sweep(h, A, M.fwd, x, b, c.omega, sor);
+    if (c.sweep == 2 || c.sweep == 3) launch_sweep(h, A, M.bwd, x, b, c.omega, sor);
+  }
+}
+
+static void norm2_async(H* h, int64_t n, const double* v, double* out_dev) {
+  dot_partial_kernel<<<kRedBlocks, kThreads, 0, h->stream>>>(n, v, v, h->partial);
+  count_launch(h);
+  reduce_final_kernel<<<1, kThreads, 0, h->stream>>>(kRedBlocks, h->partial, out_dev, 1);
+  count_launch(h);
+}
+static void dot_async(H* h, int64_t n, const double* a, const double* b, double* out_dev) {
+  dot_partial_kernel<<<kRedBlocks, kThreads, 0, h->stream>>>(n, a, b, h->partial);
+  count_launch(h);
+  reduce_final_kernel<<<1, kThreads, 0, h->stream>>>(kRedBlocks, h->partial, out_dev, 0);
+  count_launch(h);
+}
+static double read_scalar(H* h, const double* dev) {
+  CUDA_OK(cudaMemcpyAsync(h->h_scalars, dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  return h->h_scalars[0];
+}
+
+static void coarse_solve(H* h, double* x, const double* b) {
+  if (h->nfinal == 0) return;
+  dense_gemv_kernel<<<grid_for(h->nfinal), kThreads, 0, h->stream>>>((int)h->nfinal, h->coarse_inv, b, x);
+  count_launch(h);
+}
+
+// ------------------------------------------------------------------------------------------
+// the cycle: __solve!(x, ml, cycle, b, lvl)  — src/multilevel.jl:214-239, recursion :200-212
+// ------------------------------------------------------------------------------------------
+struct PhaseTimer {
+  H* h;
+  int slot;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PhaseTimer(H* h_, int lvl, int phase) : h(h_), slot(lvl * 6 + phase) {
+    if (h->profiling) {
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      cudaEventRecord(e0, h->stream);
+    }
+  }
+  ~PhaseTimer() {
+    if (h->profiling) {
+      cudaEventRecord(e1, h->stream);
+      cudaEventSynchronize(e1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (h->prof_ms && slot < (int)h->prof_ms->size()) (*h->prof_ms)[slot] += ms;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+  }
+};
+
+static void solve_level(H* h, double* x, int cycle, const double* b, int lvl, bool x_is_zero) {
+  Level& L = *h->levels[lvl];
+  { PhaseTimer t(h, lvl, 0); smooth(h, L.M, L.pre, x, b, L.temp, x_is_zero); }                    // :216
+  { PhaseTimer t(h, lvl, 1); residual(h, L.M.A, x, b, L.res); }                                  // :219-220
+  { PhaseTimer t(h, lvl, 2); spmv(h, L.R, L.res, L.coarse_b); }                                  // :223
+  CUDA_OK(cudaMemsetAsync(L.coarse_x, 0, sizeof(double) * (size_t)std::max<int64_t>(L.nc, 1), h->stream));  // :226
+  if (lvl == (int)h->levels.size() - 1) {
+    PhaseTimer t(h, lvl, 3);
+    coarse_solve(h, L.coarse_x, L.coarse_b);                                                     // :228
+  } else if (cycle == B200AMG_CYCLE_V) {
+    solve_level(h, L.coarse_x, B200AMG_CYCLE_V, L.coarse_b, lvl + 1, true);                       // :200-202
+  } else if (cycle == B200AMG_CYCLE_W) {
+    solve_level(h, L.coarse_x, B200AMG_CYCLE_W, L.coarse_b, lvl + 1, true);                       // :204-207
+    solve_level(h, L.coarse_x, B200AMG_CYCLE_W, L.coarse_b, lvl + 1, false);
+  } else {
+    solve_level(h, L.coarse_x, B200AMG_CYCLE_F, L.coarse_b, lvl + 1, true);                       // :209-212
+    solve_level(h, L.coarse_x, B200AMG_CYCLE_V, L.coarse_b, lvl + 1, false);
+  }
+  { PhaseTimer t(h, lvl, 4); spmv_add(h, L.P, L.coarse_x, x); }                                  // :233-234
+  { PhaseTimer t(h, lvl, 5); smooth(h, L.M, L.post, x, b, L.temp, false); }                      // :236
+}
+
+// one "iteration body" of _solve! on the internal level-0 vectors (multilevel.jl:179-183)
+static void cycle_body(H* h, int cycle, bool x_is_zero) {
+  if (h->levels.empty()) coarse_solve(h, h->x0, h->b0);
+  else solve_level(h, h->x0, cycle, h->b0, 0, x_is_zero);
+}
+
+static int64_t estimate_launches(H* h, int cycle, int lvl) {
+  if (h->levels.empty()) return 1;
+  const Level& L = *h->levels[lvl];
+  auto sm = [&](const SmootherCfg& c) -> int64_t {
+    if (c.kind == 0) return 0;
+    if (c.kind == B200AMG_SMOOTHER_JACOBI) return c.iter + 1;
+    int64_t per = 0;
+    if (c.sweep == 1 || c.sweep == 3) per += (int64_t)L.M.fwd.items.size();
+    if (c.sweep == 2 || c.sweep == 3) per += (int64_t)L.M.bwd.items.size();
+    return per * c.iter;
+  };
+  int64_t n = sm(L.pre) + sm(L.post) + 4;
+  if (lvl == (int)h->levels.size() - 1) return n + 1;
+  if (cycle == B200AMG_CYCLE_V) return n + estimate_launches(h, cycle, lvl + 1);
+  if (cycle == B200AMG_CYCLE_W) return n + 2 * estimate_launches(h, cycle, lvl + 1);
+  return n + estimate_launches(h, B200AMG_CYCLE_F, lvl + 1) + estimate_launches(h, B200AMG_CYCLE_V, lvl + 1);
+}
+
+static const int64_t kMaxGraphNodes = 150000;
+
+static void ensure_cycle_graph(H* h, int cycle) {
+  if (!h->use_graphs || h->cycle_graph[cycle] || h->cycle_graph_launches[cycle] < 0) return;
+  if (estimate_launches(h, cycle, 0) > kMaxGraphNodes) { h->cycle_graph_launches[cycle] = -1; return; }
+  cudaGraph_t g = nullptr;
+  h->capturing = true;
+  h->capture_count = 0;
+  CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    cycle_body(h, cycle, false);
+  } catch (...) {
+    cudaStreamEndCapture(h->stream, &g);
+    if (g) cudaGraphDestroy(g);
+    h->capturing = false;
+    throw;
+  }
+  CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+  h->capturing = false;
+  CUDA_OK(cudaGraphInstantiate(&h->cycle_graph[cycle], g, 0));
+  CUDA_OK(cudaGraphDestroy(g));
+  h->cycle_graph_launches[cycle] = h->capture_count;
+}
+
+static void run_cycle(H* h, int cycle) {
+  ensure_cycle_graph(h, cycle);
+  if (h->cycle_graph[cycle]) {
+    CUDA_OK(cudaGraphLaunch(h->cycle_graph[cycle], h->stream));
+    h->launches += h->cycle_graph_launches[cycle];
+  } else {
+    cycle_body(h, cycle, false);
+  }
+}
+
+// res = b0 - A x0 ; scalars[0] = ||res||      (multilevel.jl:188-190)
+static void residual_norm(H* h) {
+  const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
+  double* res = h->levels.empty() ? h->res_final : h->levels[0]->res;
+  residual(h, A, h->x0, h->b0, res);
+  norm2_async(h, h->n0, res, h->scalars);
+}
+
+// ------------------------------------------------------------------------------------------
+// API helpers
+// ------------------------------------------------------------------------------------------
+static void set_device(H* h) { CUDA_OK(cudaSetDevice(h->device)); }
+static void check_ready(H* h) {
+  REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  REQUIRE(h->finalized, B200AMG_ERR_STATE, "hierarchy not finalized (call b200amg_finalize first)");
+  set_device(h);
+}
+static void to_dev(H* h, double* dst, const double* src, int64_t n, int memkind) {
+  if (n == 0) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * n, memkind == B200AMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice,
+                          h->stream));
+}
+static void from_dev(H* h, double* dst, const double* src, int64_t n, int memkind) {
+  if (n == 0) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * n, memkind == B200AMG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                          h->stream));
+}
+// scratch device vector big enough for any level-sized temporary used by the entry points
+struct Scratch {
+  double* p = nullptr;
+  explicit Scratch(int64_t n) { p = dev_alloc<double>(n); }
+  ~Scratch() { cudaFree(p); }
+};
+
+extern "C" {
+
+const char* b200amg_last_error(void) { return g_err.c_str(); }
+int32_t b200amg_version(void) { return B200AMG_VERSION; }
+int32_t b200amg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
+  API_BEGIN
+  REQUIRE(out, B200AMG_ERR_BAD_ARG, "null out pointer");
+  *out = nullptr;
+  const int ndev = b200amg_device_count();
+  REQUIRE(ndev > 0, B200AMG_ERR_NO_DEVICE, "no CUDA device visible: the solve phase has no CPU fallback");
+  REQUIRE(device >= 0 && device < ndev, B200AMG_ERR_BAD_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+  std::unique_ptr<H> h(new H());
+  h->device = device;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->partial = dev_alloc<double>(kRedBlocks);
+  h->scalars = dev_alloc<double>(16);
+  CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * 16));
+  *out = h.release();
+  API_END
+}
+
+int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R,
+                          const b200amg_smoother_t* pre, const b200amg_smoother_t* post, int32_t symmetry) {
+  API_BEGIN
+  REQUIRE(h && A && P && R, B200AMG_ERR_BAD_ARG, "null argument");
+  REQUIRE(!h->finalized, B200AMG_ERR_STATE, "hierarchy already finalized");
+  REQUIRE(symmetry == B200AMG_SYMMETRY_HERMITIAN || symmetry == B200AMG_SYMMETRY_NONE, B200AMG_ERR_BAD_ARG, "bad symmetry tag");
+  REQUIRE(A->m == A->n, B200AMG_ERR_DIM_MISMATCH, "A must be square (%lld x %lld)", (long long)A->m, (long long)A->n);
+  set_device(h);
+  std::unique_ptr<Level> L(new Level());
+  L->n = A->n;
+  L->pre = to_cfg(pre);
+  L->post = to_cfg(post);
+  if (!h->levels.empty())
+    REQUIRE(h->levels.back()->nc == L->n, B200AMG_ERR_DIM_MISMATCH, "level has %lld rows but the previous level coarsens to %lld",
+            (long long)L->n, (long long)h->levels.back()->nc);
+  {
+    HostCsr hP = stage_operator_by_rows(P);
+    HostCsr hR = stage_operator_by_rows(R);
+    REQUIRE(hP.nrows == L->n, B200AMG_ERR_DIM_MISMATCH, "P has %lld rows, A has %lld", (long long)hP.nrows, (long long)L->n);
+    REQUIRE(hR.ncols == L->n, B200AMG_ERR_DIM_MISMATCH, "R has %lld columns, A has %lld", (long long)hR.ncols, (long long)L->n);
+    REQUIRE(hR.nrows == hP.ncols, B200AMG_ERR_DIM_MISMATCH, "R has %lld rows but P has %lld columns", (long long)hR.nrows,
+            (long long)hP.ncols);
+    L->nc = hR.nrows;
+    L->P.upload(hP);
+    L->R.upload(hR);
+  }
+  {
+    HostCsr hAt = stage_csc_as_rows_of_transpose(A);
+    L->M.build(hAt, symmetry, cfg_needs_fwd(L->pre) || cfg_needs_fwd(L->post), cfg_needs_bwd(L->pre) || cfg_needs_bwd(L->post), true);
+  }
+  L->res = dev_alloc<double>(L->n);
+  L->temp = dev_alloc<double>(L->n);
+  L->coarse_x = dev_alloc<double>(L->nc);
+  L->coarse_b = dev_alloc<double>(L->nc);
+  h->levels.push_back(std::move(L));
+  API_END
+}
+
+int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n, const double* inv) {
+  API_BEGIN
+  REQUIRE(h && final_A, B200AMG_ERR_BAD_ARG, "null argument");
+  REQUIRE(!h->finalized, B200AMG_ERR_STATE, "hierarchy already finalized");
+  REQUIRE(final_A->m == n && final_A->n == n, B200AMG_ERR_DIM_MISMATCH, "final_A is %lld x %lld, coarse operator is %lld",
+          (long long)final_A->m, (long long)final_A->n, (long long)n);
+  REQUIRE(n == 0 || inv, B200AMG_ERR_BAD_ARG, "null coarse operator");
+  REQUIRE(n <= 16384, B200AMG_ERR_UNSUPPORTED, "dense coarse operator limited to 16384 rows (got %lld)", (long long)n);
+  if (!h->levels.empty())
+    REQUIRE(h->levels.back()->nc == n, B200AMG_ERR_DIM_MISMATCH, "coarsest matrix has %lld rows, last level coarsens to %lld",
+            (long long)n, (long long)h->levels.back()->nc);
+  set_device(h);
+  HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
+  h->finalA.upload(transpose(hAt));
+  h->nfinal = n;
+  std::vector<double> m(inv, inv + n * n);
+  h->coarse_inv = dev_upload(m);
+  h->res_final = dev_alloc<double>(n);
+  h->have_coarse = true;
+  API_END
+}
+
+int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_size, const void* id, int64_t id_bytes) {
+  (void)h; (void)rank; (void)id; (void)id_bytes;
+  if (world_size == 1) return B200AMG_OK;
+  return fail(B200AMG_ERR_UNSUPPORTED, "row-partitioned fine level not available in this build");
+}
+
+int32_t b200amg_finalize(b200amg_handle_t h) {
+  API_BEGIN
+  REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  REQUIRE(!h->finalized, B200AMG_ERR_STATE, "hierarchy already finalized");
+  REQUIRE(h->have_coarse, B200AMG_ERR_STATE, "b200amg_set_coarse has not been called");
+  set_device(h);
+  h->n0 = h->levels.empty() ? h->nfinal : h->levels[0]->n;
+  h->x0 = dev_alloc<double>(h->n0);
+  h->b0 = dev_alloc<double>(h->n0);
+  CUDA_OK(cudaMemset(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1)));
+  CUDA_OK(cudaMemset(h->b0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1)));
+  h->finalized = true;
+  API_END
+}
+
+int32_t b200amg_destroy(b200amg_handle_t h) {
+  if (!h) return B200AMG_OK;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto& L : h->levels) {
+    L->M.release(); L->P.release(); L->R.release();
+    cudaFree(L->res); cudaFree(L->temp); cudaFree(L->coarse_x); cudaFree(L->coarse_b);
+  }
+  h->finalA.release();
+  cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
+  cudaFree(h->partial); cudaFree(h->scalars); cudaFreeHost(h->h_scalars);
+  cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush);
+  for (int c = 0; c < 3; ++c)
+    if (h->cycle_graph[c]) cudaGraphExecDestroy(h->cycle_graph[c]);
+  if (h->resnorm_graph) cudaGraphExecDestroy(h->resnorm_graph);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return B200AMG_OK;
+}
+
+// _solve!  — src/multilevel.jl:158-198
+int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t maxiter, double abstol,
+                      double reltol, int32_t calculate_residual, double* residuals, int32_t cap, int32_t* nres,
+                      int32_t* iters, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  const int64_t n = h->n0;
+  to_dev(h, h->b0, b, n, memkind);
+  to_dev(h, h->x0, x, n, memkind);
+  int nr = 0;
+  norm2_async(h, n, h->b0, h->scalars);
+  double normb = read_scalar(h, h->scalars), normres = normb;                        // :170
+  if (normb != 0) abstol = std::max(reltol * normb, abstol);                           // :171-173
+  if (residuals && nr < cap) residuals[nr++] = normb;                                  // :174
+  int itr = 1;
+  while (itr <= maxiter && (!calculate_residual || normres > abstol)) {                // :178
+    run_cycle(h, cycle);                                                               // :179-183
+    if (calculate_residual) {
+      residual_norm(h);                                                                // :188-190
+      normres = read_scalar(h, h->scalars);
+      if (residuals && nr < cap) residuals[nr++] = normres;                            // :191
+    }
+    itr += 1;
+  }
+  from_dev(h, x, h->x0, n, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (nres) *nres = nr;
+  if (iters) *iters = itr - 1;
+  API_END
+}
+
+int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  to_dev(h, h->b0, b, h->n0, memkind);
+  to_dev(h, h->x0, x, h->n0, memkind);
+  run_cycle(h, cycle);
+  from_dev(h, x, h->x0, h->n0, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+// ldiv!(x, p, b)  — src/preconditioner.jl:12-19
+int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t init_zero, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  to_dev(h, h->b0, b, h->n0, memkind);
+  if (init_zero) CUDA_OK(cudaMemsetAsync(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1), h->stream));
+  else CUDA_OK(cudaMemcpyAsync(h->x0, h->b0, sizeof(double) * h->n0, cudaMemcpyDeviceToDevice, h->stream));
+  run_cycle(h, cycle);
+  from_dev(h, x, h->x0, h->n0, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double* x, const double* b, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(level >= 0 && level < (int)h->levels.size(), B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  Level& L = *h->levels[level];
+  Scratch sx(L.n), sb(L.n);
+  to_dev(h, sx.p, x, L.n, memkind);
+  to_dev(h, sb.p, b, L.n, memkind);
+  smooth(h, L.M, which == B200AMG_PRE ? L.pre : L.post, sx.p, sb.p, L.temp, false);
+  from_dev(h, x, sx.p, L.n, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_apply(b200amg_handle_t h, int32_t level, int32_t op, double* y, const double* x, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(y && x, B200AMG_ERR_BAD_ARG, "null vector");
+  const int nl = (int)h->levels.size();
+  const DevCsr* A = nullptr;
+  if (level == nl && op == B200AMG_OP_A) A = &h->finalA;
+  else {
+    REQUIRE(level >= 0 && level < nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+    Level& L = *h->levels[level];
+    A = op == B200AMG_OP_A ? &L.M.A : op == B200AMG_OP_P ? &L.P : op == B200AMG_OP_R ? &L.R : nullptr;
+    REQUIRE(A, B200AMG_ERR_BAD_ARG, "unknown operator %d", op);
+  }
+  Scratch sx(A->ncols), sy(A->nrows);
+  to_dev(h, sx.p, x, A->ncols, memkind);
+  spmv(h, *A, sx.p, sy.p);
+  from_dev(h, y, sy.p, A->nrows, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_residual(b200amg_handle_t h, int32_t level, double* r, const double* b, const double* x, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(r && b && x, B200AMG_ERR_BAD_ARG, "null vector");
+  const int nl = (int)h->levels.size();
+  REQUIRE(level >= 0 && level <= nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  const DevCsr& A = level == nl ? h->finalA : h->levels[level]->M.A;
+  Scratch sx(A.ncols), sb(A.nrows), sr(A.nrows);
+  to_dev(h, sx.p, x, A.ncols, memkind);
+  to_dev(h, sb.p, b, A.nrows, memkind);
+  residual(h, A, sx.p, sb.p, sr.p);
+  from_dev(h, r, sr.p, A.nrows, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_coarse_solve(b200amg_handle_t h, double* x, const double* b, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  Scratch sx(h->nfinal), sb(h->nfinal);
+  to_dev(h, sb.p, b, h->nfinal, memkind);
+  coarse_solve(h, sx.p, sb.p);
+  from_dev(h, x, sx.p, h->nfinal, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_norm(b200amg_handle_t h, int64_t n, const double* v, double* out, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(v && out && n >= 0, B200AMG_ERR_BAD_ARG, "bad argument");
+  if (memkind == B200AMG_MEM_HOST) {
+    Scratch s(n);
+    to_dev(h, s.p, v, n, memkind);
+    norm2_async(h, n, s.p, h->scalars);
+    *out = read_scalar(h, h->scalars);
+  } else {
+    norm2_async(h, n, v, h->scalars);
+    *out = read_scalar(h, h->scalars);
+  }
+  API_END
+}
+
+// Device-resident left-preconditioned CG (IterativeSolvers' PCGIterable with Pl = one AMG cycle):
+//   c = Pl \ r ; rho = c.r ; u = c + (rho/rho_prev) u ; q = A u ; alpha = rho/(u.q) ; x += alpha u ; r -= alpha q
+// r lives in b0 and c in x0, so the preconditioner is zero-fill + the captured cycle graph with no copies.
+int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t maxiter, double abstol,
+                    double reltol, double* residuals, int32_t cap, int32_t* nres, int32_t* iters, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  const int64_t n = h->n0;
+  const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
+  if (!h->pcg_u) { h->pcg_u = dev_alloc<double>(n); h->pcg_q = dev_alloc<double>(n); h->pcg_x = dev_alloc<double>(n); }
+  double* S = h->scalars;  // [0] norm [1] rho [2] rho_prev [3] uq
+  to_dev(h, h->b0, b, n, memkind);                                                       // r = b (x starts at zero)
+  CUDA_OK(cudaMemsetAsync(h->pcg_x, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), h->stream));
+  CUDA_OK(cudaMemsetAsync(h->pcg_u, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), h->stream));
+  set_scalar_kernel<<<1, 32, 0, h->stream>>>(S + 1, 1.0);
+  count_launch(h);
+  norm2_async(h, n, h->b0, S);
+  double residual = read_scalar(h, S);
+  const double tol = std::max(reltol * residual, abstol);
+  int nr = 0, it = 0;
+  if (residuals && nr < cap) residuals[nr++] = residual;
+  const unsigned g = grid_for(n);
+  while (!(it >= maxiter || residual <= tol)) {
+    CUDA_OK(cudaMemsetAsync(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), h->stream));  // ldiv!: x .= 0
+    run_cycle(h, cycle);                                                                 // c = Pl \ r   (c == x0, r == b0)
+    copy_scalar_kernel<<<1, 32, 0, h->stream>>>(S + 2, S + 1);
+    count_launch(h);
+    dot_async(h, n, h->x0, h->b0, S + 1);                                                // rho = c.r
+    pcg_update_u_kernel<<<g, kThreads, 0, h->stream>>>(n, h->x0, h->pcg_u, S + 1, S + 2);
+    count_launch(h);
+    spmv(h, A, h->pcg_u, h->pcg_q);                                                      // q = A u
+    dot_async(h, n, h->pcg_u, h->pcg_q, S + 3);                                          // u.q
+    pcg_update_xr_kernel<<<g, kThreads, 0, h->stream>>>(n, h->pcg_x, h->b0, h->pcg_u, h->pcg_q, S + 1, S + 3);
+    count_launch(h);
+    norm2_async(h, n, h->b0, S);
+    residual = read_scalar(h, S);
+    if (residuals && nr < cap) residuals[nr++] = residual;
+    ++it;
+  }
+  from_dev(h, x, h->pcg_x, n, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (nres) *nres = nr;
+  if (iters) *iters = it;
+  API_END
+}
+
+// ---- standalone smoothers -----------------------------------------------------------------
+struct b200amg_smoother_obj {
+  H* h = nullptr;   // private mini-handle (stream, counters)
+  SmootherMatrix M;
+  SmootherCfg cfg;
+  double *x = nullptr, *b = nullptr, *temp = nullptr;
+};
+
+int32_t b200amg_smoother_create(b200amg_smoother_handle_t* out, int32_t device, const b200amg_csc_t* A,
+                                const b200amg_smoother_t* config, int32_t symmetry) {
+  API_BEGIN
+  REQUIRE(out && A && config, B200AMG_ERR_BAD_ARG, "null argument");
+  *out = nullptr;
+  REQUIRE(A->m == A->n, B200AMG_ERR_DIM_MISMATCH, "A must be square");
+  REQUIRE(symmetry == B200AMG_SYMMETRY_HERMITIAN || symmetry == B200AMG_SYMMETRY_NONE, B200AMG_ERR_BAD_ARG, "bad symmetry tag");
+  b200amg_handle_t hh = nullptr;
+  int32_t rc = b200amg_create(&hh, device);
+  if (rc) throw AmgError{rc, g_err};
+  std::unique_ptr<b200amg_smoother_obj> s(new b200amg_smoother_obj());
+  s->h = hh;
+  try {
+    s->cfg = to_cfg(config);
+    HostCsr hAt = stage_csc_as_rows_of_transpose(A);
+    s->M.build(hAt, symmetry, cfg_needs_fwd(s->cfg), cfg_needs_bwd(s->cfg), false);
+    s->x = dev_alloc<double>(A->n);
+    s->b = dev_alloc<double>(A->n);
+    s->temp = dev_alloc<double>(A->n);
+  } catch (...) {
+    s->M.release(); cudaFree(s->x); cudaFree(s->b); cudaFree(s->temp);
+    b200amg_destroy(hh);
+    throw;
+  }
+  *out = s.release();
+  API_END
+}
+
+int32_t b200amg_smoother_apply(b200amg_smoother_handle_t s, double* x, const double* b, int32_t memkind) {
+  API_BEGIN
+  REQUIRE(s && x && b, B200AMG_ERR_BAD_ARG, "null argument");
+  H* h = s->h;
+  set_device(h);
+  to_dev(h, s->x, x, s->M.n, memkind);
+  to_dev(h, s->b, b, s->M.n, memkind);
+  smooth(h, s->M, s->cfg, s->x, s->b, s->temp, false);
+  from_dev(h, x, s->x, s->M.n, memkind);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END
+}
+
+int32_t b200amg_smoother_destroy(b200amg_smoother_handle_t s) {
+  if (!s) return B200AMG_OK;
+  cudaSetDevice(s->h->device);
+  cudaStreamSynchronize(s->h->stream);
+  s->M.release();
+  cudaFree(s->x); cudaFree(s->b); cudaFree(s->temp);
+  b200amg_destroy(s->h);
+  delete s;
+  return B200AMG_OK;
+}
+
+// ---- introspection / measurement ----------------------------------------------------------
+int32_t b200amg_num_levels(b200amg_handle_t h) { return h ? (int32_t)h->levels.size() + 1 : 0; }
+
+int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_t* nnz_a, int64_t* nnz_p, int64_t* wavefronts) {
+  API_BEGIN
+  REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  const int nl = (int)h->levels.size();
+  REQUIRE(level >= 0 && level <= nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  if (level == nl) {
+    if (n) *n = h->nfinal;
+    if (nnz_a) *nnz_a = h->finalA.nnz;
+    if (nnz_p) *nnz_p = 0;
+    if (wavefronts) *wavefronts = 0;
+  } else {
+    Level& L = *h->levels[level];
+    if (n) *n = L.n;
+    if (nnz_a) *nnz_a = L.M.At.nnz;
+    if (nnz_p) *nnz_p = L.P.nnz;
+    if (wavefronts) *wavefronts = L.M.fwd.built ? L.M.fwd.nlev : (L.M.bwd.built ? L.M.bwd.nlev : 0);
+  }
+  API_END
+}
+
+int64_t b200amg_launch_count(b200amg_handle_t h) { return h ? h->launches : 0; }
+
+int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int32_t cycle, int32_t reps, int32_t flush_l2,
+                            double* ms) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(ms && reps > 0, B200AMG_ERR_BAD_ARG, "bad argument");
+  const int nl = (int)h->levels.size();
+  REQUIRE(what == 5 || what == 6 || (level >= 0 && level < nl), B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  if (flush_l2 && !h->flush) {
+    h->flush_bytes = (size_t)512 << 20;
+    CUDA_OK(cudaMalloc(&h->flush, h->flush_bytes));
+  }
+  if (what == 5) ensure_cycle_graph(h, cycle);
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    if (flush_l2) CUDA_OK(cudaMemsetAsync(h->flush, r & 0xff, h->flush_bytes, h->stream));
+    CUDA_OK(cudaEventRecord(e0, h->stream));
+    if (what == 5) {
+      run_cycle(h, cycle);
+    } else if (what == 6) {
+      norm2_async(h, h->n0, h->b0, h->scalars + 4);
+    } else {
+      Level& L = *h->levels[level];
+      // level > 0: the level's x / b are the parent's coarse_x / coarse_b
+      double* x = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
+      const double* b = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
+      switch (what) {
+        case 0: spmv(h, L.M.A, x, L.res); break;
+        case 1: residual(h, L.M.A, x, b, L.res); break;
+        case 2: smooth(h, L.M, L.pre, x, b, L.temp, false); break;
+        case 3: spmv(h, L.R, L.res, L.coarse_b); break;
+        case 4: spmv_add(h, L.P, L.coarse_x, x); break;
+        default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown kernel selector %d", what);
+      }
+    }
+    CUDA_OK(cudaEventRecord(e1, h->stream));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t = 0;
+    CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+    total += t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms = total / reps;
+  API_END
+}
+
+int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int32_t cap) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(ms && cap >= 6 * ((int)h->levels.size() + 1), B200AMG_ERR_BAD_ARG, "ms buffer too small");
+  std::vector<double> acc((size_t)cap, 0.0);
+  h->profiling = true;
+  h->prof_ms = &acc;
+  try {
+    cycle_body(h, cycle, false);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+  } catch (...) {
+    h->profiling = false; h->prof_ms = nullptr;
+    throw;
+  }
+  h->profiling = false;
+  h->prof_ms = nullptr;
+  for (int i = 0; i < cap; ++i) ms[i] = acc[i];
+  API_END
+}
+
+int32_t b200amg_device_vectors(b200amg_handle_t h, double** x, double** b) {
+  API_BEGIN
+  check_ready(h);
+  if (x) *x = h->x0;
+  if (b) *b = h->b0;
+  API_END
+}
+
+}  // extern "C"

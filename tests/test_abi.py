@@ -1,0 +1,57 @@
+"""CPU-side checks of the C-ABI boundary: the library loads, exports every symbol that
+include/b200amg.h declares, and refuses to compute without a device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200amg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200amg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(amg):
+    from algebraicmultigrid_jl_b200 import _devlib
+
+    _devlib.build()
+    L = _devlib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 27
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted(_devlib.SYMBOLS) == declared
+    assert L.b200amg_version() == 100
+
+
+def test_no_device_is_an_error_not_a_fallback(amg):
+    from algebraicmultigrid_jl_b200 import _devlib
+
+    if _devlib.device_count() > 0:
+        return
+    h = C.c_void_p()
+    rc = _devlib.lib().b200amg_create(C.byref(h), 0)
+    assert rc == -9 and not h.value
+    assert b"no CPU fallback" in _devlib.lib().b200amg_last_error()
+    A = amg.poisson(100)
+    ml = amg.ruge_stuben(A)
+    try:
+        amg._solve(ml, np.ones(100))
+    except _devlib.B200AmgError as e:
+        assert e.code == -9
+    else:
+        raise AssertionError("the solve phase ran without a GPU")
+
+
+def test_null_and_state_errors(amg):
+    from algebraicmultigrid_jl_b200 import _devlib
+
+    L = _devlib.lib()
+    assert L.b200amg_create(None, 0) == -1
+    assert L.b200amg_finalize(None) == -1
+    assert L.b200amg_destroy(None) == 0
+    assert L.b200amg_num_levels(None) == 0

@@ -1,0 +1,376 @@
+"""GPU parity: the CUDA engine (through the C-ABI, via the host mirror of the reference API) against
+the CPU oracle on the same seeded inputs, against the reference's golden vectors, and through
+size-independent properties at larger sizes.
+
+Stated fp64 tolerances (relative, infinity norm unless noted):
+  single kernel (SpMV / residual / restriction / prolongation / Jacobi)   1e-13
+  Gauss-Seidel / SOR sweeps (wavefront order == lexicographic order)        1e-12
+  one V/W/F cycle                                                           1e-11
+  _solve: identical iteration count, residual history 1e-6 per entry, final x 1e-9 (2-norm)
+The only source of difference is the summation order inside a row (lane-strided partial sums +
+shuffle tree, FMA contraction) — the update order of Gauss-Seidel is the reference's.
+"""
+import numpy as np
+import pytest
+
+import goldens
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_KERNEL, TOL_SWEEP, TOL_CYCLE, TOL_SOLVE_X, TOL_HIST = 1e-13, 1e-12, 1e-11, 1e-9, 1e-6
+
+
+def relinf(a, b):
+    d = np.abs(np.asarray(a) - np.asarray(b)).max() if len(a) else 0.0
+    s = np.abs(b).max() if len(b) else 0.0
+    return d / s if s > 0 else d
+
+
+def _rng(seed=0):
+    return np.random.default_rng(seed)
+
+
+def _thing_b():
+    b = np.zeros(46)
+    b[0], b[1] = 1, -1
+    return b
+
+
+@pytest.fixture(scope="module")
+def jac(amg):
+    return amg.Jacobi(2.0 / 3.0)
+
+
+# ---- single kernels --------------------------------------------------------------------------
+@pytest.mark.parametrize("dims", [(1000,), (50, 50), (17, 9, 13), (64, 64, 64)])
+def test_spmv_residual_restrict_prolong(amg, dims):
+    A = amg.poisson(dims if len(dims) > 1 else dims[0])
+    for ml in (amg.ruge_stuben(A), amg.smoothed_aggregation(A)):
+        dev = ml.device()
+        r = _rng(1)
+        for lv, level in enumerate(ml.levels):
+            n, nc = level.A.n, level.R.shape[0]
+            x, b, xc = r.standard_normal(n), r.standard_normal(n), r.standard_normal(nc)
+            y = dev.apply(lv, 0, np.empty(n), x)
+            assert relinf(y, oracle.mul(level.A, x)) <= TOL_KERNEL
+            res = dev.residual(lv, np.empty(n), b, x)
+            assert relinf(res, b - oracle.mul(level.A, x)) <= TOL_KERNEL
+            Rst, Radj = oracle.oracle._storage(level.R)
+            Pst, Padj = oracle.oracle._storage(level.P)
+            assert relinf(dev.apply(lv, 2, np.empty(nc), x), oracle.mul(Rst, x, adjoint=bool(Radj))) <= TOL_KERNEL
+            assert relinf(dev.apply(lv, 1, np.empty(n), xc), oracle.mul(Pst, xc, adjoint=bool(Padj))) <= TOL_KERNEL
+        nf = ml.final_A.n
+        xf = r.standard_normal(nf)
+        assert relinf(dev.apply(len(ml.levels), 0, np.empty(nf), xf), oracle.mul(ml.final_A, xf)) <= TOL_KERNEL
+        assert relinf(dev.coarse_solve(np.empty(nf), xf), ml.coarse_solver.dense_operator() @ xf) <= 1e-12
+        assert abs(dev.norm(x) - oracle.norm(x)) <= 1e-14 * oracle.norm(x)
+        ml.release()
+
+
+def test_spmv_nonsymmetric_uses_true_A(amg, fx):
+    A = fx.sprand_plus_diag(300, 0.03, 5.0, seed=7)
+    ml = amg.ruge_stuben(A, symmetry=amg.NoSymmetry())
+    x = _rng(2).standard_normal(300)
+    y = ml.device().apply(0, 0, np.empty(300), x)
+    assert relinf(y, A.to_scipy() @ x) <= TOL_KERNEL
+    ml.release()
+
+
+# ---- smoothers ---------------------------------------------------------------------------------
+def test_gauss_seidel_known_answers_on_device(amg):
+    # test/sa_tests.jl:316-379 — exact rationals, bit-for-bit
+    fwd, bwd = amg.GaussSeidel(amg.ForwardSweep()), amg.GaussSeidel(amg.BackwardSweep())
+    A1, A3 = amg.poisson(1), amg.poisson(3)
+
+    def run(s, A, x, b):
+        x = np.array(x, dtype=float)
+        s(A, x, np.array(b, dtype=float))
+        return x
+
+    assert np.array_equal(run(fwd, A1, [0.0], [0.0]), [0.0])
+    assert np.array_equal(run(fwd, A3, [0.0, 1, 2], [0.0, 0, 0]), [1 / 2, 5 / 4, 5 / 8])
+    assert np.array_equal(run(bwd, A3, [0.0, 1, 2], [0.0, 0, 0]), [1 / 8, 1 / 4, 1 / 2])
+    assert np.array_equal(run(fwd, A1, [0.0], [10.0]), [5.0])
+    assert np.array_equal(run(fwd, A3, [0.0, 1, 2], [10.0, 20, 30]), [11 / 2, 55 / 4, 175 / 8])
+    A100 = amg.poisson(100)
+    x1 = run(amg.GaussSeidel(amg.ForwardSweep(), 200), A100, np.ones(100), np.zeros(100))
+    x2 = run(amg.GaussSeidel(amg.BackwardSweep(), 200), A100, np.ones(100), np.zeros(100))
+    r1, r2 = np.linalg.norm(A100.matvec(x1)), np.linalg.norm(A100.matvec(x2))
+    assert r1 < 0.01 and r2 < 0.01 and np.isclose(r1, r2)
+
+
+def test_regression_26_on_device(amg):
+    x = np.ones(10)
+    amg.GaussSeidel(amg.SymmetricSweep(), 4)(amg.poisson(10), x, np.zeros(10))
+    assert np.sum((x - goldens.SGS4_POISSON10) ** 2) < 1e-6
+
+
+def _smoother_zoo(amg):
+    F_, B_, S_ = amg.ForwardSweep(), amg.BackwardSweep(), amg.SymmetricSweep()
+    return [amg.Jacobi(4 / 5, iter=2), amg.Jacobi(2 / 3), amg.GaussSeidel(F_), amg.GaussSeidel(B_), amg.GaussSeidel(S_, 2),
+            amg.SOR(0.5, F_), amg.SOR(0.5, B_), amg.SOR(1.3, S_, 2)]
+
+
+@pytest.mark.parametrize("case", ["poisson1d", "poisson2d", "poisson3d", "rs_coarse", "thing", "nonsym"])
+@pytest.mark.parametrize("symmetry", ["hermitian", "none"])
+def test_smoothers_vs_oracle(amg, fx, case, symmetry):
+    if case == "poisson1d":
+        A = amg.poisson(777)
+    elif case == "poisson2d":
+        A = amg.poisson((40, 33))
+    elif case == "poisson3d":
+        A = amg.poisson((20, 17, 12))
+    elif case == "rs_coarse":
+        A = amg.ruge_stuben(amg.poisson((24, 24, 24))).levels[1].A     # irregular, ~18 nnz/row, symmetric to rounding only
+    elif case == "thing":
+        A = fx.matrix("thing")
+    else:
+        A = fx.sprand_plus_diag(400, 0.02, 5.0, seed=11)
+    sym = amg.HermitianSymmetry() if symmetry == "hermitian" else amg.NoSymmetry()
+    r = _rng(5)
+    x0, b = r.standard_normal(A.n), r.standard_normal(A.n)
+    for sm in _smoother_zoo(amg):
+        x = x0.copy()
+        sm(A, x, b, sym)
+        ref = oracle.smooth(A, sm, x0.copy(), b, symmetry=symmetry)
+        tol = TOL_KERNEL if sm.kind == "jacobi" else TOL_SWEEP
+        assert relinf(x, ref) <= tol, (case, symmetry, sm)
+
+
+def test_fast_equals_general_on_symmetric_device(amg):
+    # test/test_smoothers.jl:29-45
+    A = amg.poisson(50)
+    x0, b = _rng(3).random(50), np.ones(50)
+    for sm in [amg.Jacobi(4 / 5, iter=2), amg.GaussSeidel(amg.SymmetricSweep(), iter=2), amg.SOR(0.5, iter=2)]:
+        xf, xg = x0.copy(), x0.copy()
+        sm(A, xf, b, amg.HermitianSymmetry())
+        sm(A, xg, b, amg.NoSymmetry())
+        assert np.allclose(xf, xg), sm
+
+
+def test_nosymmetry_smoothers_converge_device(amg, fx):
+    # test/test_smoothers.jl:15-27
+    N = 50
+    A = fx.sprand_plus_diag(N, 0.05, 5.0, seed=1)
+    x0, b = _rng(2).random(N), np.ones(N)
+    for sm in [amg.Jacobi(1 / 6, iter=500), amg.GaussSeidel(amg.ForwardSweep(), 100), amg.GaussSeidel(amg.BackwardSweep(), 100),
+               amg.GaussSeidel(amg.SymmetricSweep(), 100), amg.SOR(0.5, amg.ForwardSweep(), 100),
+               amg.SOR(0.5, amg.BackwardSweep(), 100), amg.SOR(0.5, amg.SymmetricSweep(), 100)]:
+        x = x0.copy()
+        sm(A, x, b, amg.NoSymmetry())
+        assert np.allclose(A.matvec(x), b), sm
+
+
+def test_singular_exception_device(amg):
+    import scipy.sparse as sp
+
+    A = amg.SparseMatrixCSC.from_scipy(sp.csc_matrix(np.array([[1.0, 2.0], [3.0, 0.0]])))
+    with pytest.raises(amg.SingularException):
+        amg.GaussSeidel(amg.ForwardSweep())(A, np.ones(2), np.ones(2), amg.NoSymmetry())
+    # the fast variants silently skip zero diagonals (smoother.jl:87)
+    x = np.ones(2)
+    amg.GaussSeidel(amg.ForwardSweep())(A, x, np.ones(2))
+    assert np.array_equal(x, oracle.smooth(A, amg.GaussSeidel(amg.ForwardSweep()), np.ones(2), np.ones(2)))
+
+
+def test_level_smooth_entry(amg):
+    ml = amg.ruge_stuben(amg.poisson((30, 30)))
+    r = _rng(8)
+    for lv, level in enumerate(ml.levels):
+        x0, b = r.standard_normal(level.A.n), r.standard_normal(level.A.n)
+        x = ml.device().smooth(lv, 0, x0.copy(), b)
+        assert relinf(x, oracle.smooth(level.A, level.presmoother.config, x0.copy(), b)) <= TOL_SWEEP
+    ml.release()
+
+
+# ---- cycles ------------------------------------------------------------------------------------
+def _hierarchies(amg, A, jac):
+    F_ = amg.GaussSeidel(amg.ForwardSweep())
+    yield "rs-sgs", amg.ruge_stuben(A)
+    yield "rs-fgs-pinv", amg.ruge_stuben(A, presmoother=F_, postsmoother=F_, coarse_solver=amg.Pinv)
+    yield "rs-jacobi", amg.ruge_stuben(A, presmoother=jac, postsmoother=jac)
+    yield "sa-sgs", amg.smoothed_aggregation(A)
+    yield "sa-jacobi", amg.smoothed_aggregation(A, presmoother=jac, postsmoother=jac)
+    yield "sa-sor", amg.smoothed_aggregation(A, presmoother=amg.SOR(1.2), postsmoother=amg.SOR(0.9, amg.BackwardSweep(), 2))
+
+
+@pytest.mark.parametrize("dims", [(1000,), (50, 50), (20, 20, 20)])
+def test_one_cycle_vs_oracle(amg, jac, dims):
+    A = amg.poisson(dims if len(dims) > 1 else dims[0])
+    r = _rng(4)
+    b, x0 = r.random(A.n), r.standard_normal(A.n)
+    for name, ml in _hierarchies(amg, A, jac):
+        H = oracle.OracleHierarchy(ml)
+        for cyc, cname in ((amg.V(), "V"), (amg.W(), "W"), (amg.F(), "F")):
+            x = amg._solve_(x0.copy(), ml, b, cyc, maxiter=1, calculate_residual=False)
+            ref = H.solve(b, cycle=cname, x0=x0, maxiter=1, calculate_residual=False)
+            assert relinf(x, ref) <= TOL_CYCLE, (name, cname)
+            # ldiv!: zero + one cycle
+            p = amg.aspreconditioner(ml, cyc)
+            assert relinf(amg.backslash(p, b), H.precond(b, cycle=cname)) <= TOL_CYCLE, (name, cname)
+        ml.release()
+
+
+def test_solve_vs_oracle(amg, jac):
+    A = amg.poisson((50, 50))
+    b = A.matvec(np.ones(A.n))
+    for name, ml in _hierarchies(amg, A, jac):
+        H = oracle.OracleHierarchy(ml)
+        for cyc, cname in ((amg.V(), "V"), (amg.W(), "W"), (amg.F(), "F")):
+            x, hist = amg._solve(ml, b, cyc, reltol=1e-8, log=True)
+            xr, histr = H.solve(b, cycle=cname, reltol=1e-8, log=True)
+            assert len(hist) == len(histr), (name, cname, len(hist), len(histr))
+            assert np.allclose(hist, histr, rtol=TOL_HIST, atol=0), (name, cname)
+            assert np.linalg.norm(x - xr) <= TOL_SOLVE_X * np.linalg.norm(xr), (name, cname)
+            if len(hist) <= 100:                       # converged within maxiter (test/cycle_tests.jl:16)
+                assert np.linalg.norm(b - A.matvec(x)) < 1e-8 * np.linalg.norm(b)
+        ml.release()
+
+
+def test_thing_goldens_on_device(amg, fx):
+    # test/runtests.jl:143-224 — the reference's own golden vectors, Σdiff² < 1e-8
+    A = fx.matrix("thing")
+    sm = amg.GaussSeidel(amg.ForwardSweep())
+    ml = amg.ruge_stuben(A, presmoother=sm, postsmoother=sm, coarse_solver=amg.Pinv)
+    b = _thing_b()
+    x = amg._solve(ml, A.matvec(np.ones(46)), maxiter=1, abstol=1e-12)
+    assert np.sum((x - goldens.THING_ZERO_GOLDEN) ** 2) < 1e-8
+    x = amg.solve(A, b, amg.RugeStubenAMG(), presmoother=sm, postsmoother=sm, maxiter=1, abstol=1e-12, coarse_solver=amg.Pinv)
+    assert np.sum((x - goldens.THING_FWDGS_ONE_CYCLE) ** 2) < 1e-8
+    x = amg.cg(A, b, Pl=amg.aspreconditioner(ml))
+    assert np.sum((x - goldens.THING_CG_FWDGS) ** 2) < 1e-8
+    ml.release()
+    ml = amg.ruge_stuben(A, coarse_solver=amg.Pinv)
+    x = amg.cg(A, b, Pl=amg.aspreconditioner(ml), maxiter=100_000, reltol=1e-6)
+    assert np.sum((x - goldens.THING_CG_SGS) ** 2) < 1e-8
+    x = amg._solve(ml, b, maxiter=1, reltol=1e-12)
+    assert np.sum((x - goldens.THING_SGS_ONE_CYCLE) ** 2) < 1e-8
+    ml.release()
+
+
+def test_solver_poisson1000_device(amg, fx):
+    # test/runtests.jl:112-141 (config C1)
+    A = amg.poisson(1000)
+    b = A.matvec(np.ones(1000))
+    assert np.sum((amg._solve(amg.ruge_stuben(A), b) - 1) ** 2) < 1e-8
+    fs = amg.GaussSeidel(amg.ForwardSweep())
+    assert np.sum((amg._solve(amg.ruge_stuben(A, presmoother=fs, postsmoother=fs), b) - 1) ** 2) < 1e-8
+    A = fx.matrix("randlap")
+    b = A.matvec(np.ones(100))
+    assert np.sum(amg._solve(amg.ruge_stuben(A, presmoother=fs, postsmoother=fs), b) ** 2) < 1e-8
+    assert np.sum(amg._solve(amg.ruge_stuben(A), b) ** 2) < 1e-6
+
+
+def test_cycles_device(amg):
+    # test/cycle_tests.jl:6-30
+    A = amg.poisson((50, 50))
+    b = A.matvec(np.ones(A.n))
+    for method in (amg.ruge_stuben, amg.smoothed_aggregation):
+        ml = method(A)
+        for cyc in (amg.V(), amg.W(), amg.F()):
+            x = amg._solve(ml, b, cyc, reltol=1e-8)
+            assert np.linalg.norm(b - A.matvec(x)) < 1e-8 * np.linalg.norm(b)
+            x = amg.cg(A, b, Pl=amg.aspreconditioner(ml, cyc), reltol=1e-8)
+            assert np.linalg.norm(b - A.matvec(x)) <= 1e-8 * np.linalg.norm(b)
+        ml.release()
+
+
+def test_pcg_vs_oracle(amg, fx):
+    A = amg.poisson((40, 40))
+    b = _rng(9).random(A.n)
+    ml = amg.smoothed_aggregation(A)
+    H = oracle.OracleHierarchy(ml)
+    x, info = amg.cg(A, b, Pl=amg.aspreconditioner(ml), reltol=1e-10, log=True)
+    xr, histr = H.pcg(b, reltol=1e-10, log=True)
+    assert info["iters"] == H.iters
+    assert np.allclose(info["resnorm"], histr, rtol=1e-5, atol=0)
+    assert np.linalg.norm(x - xr) <= 1e-9 * np.linalg.norm(xr)
+    ml.release()
+
+
+def test_elasticity_nns_device(amg, fx):
+    # test/nns_test.jl:214-223 (config C5): converges with B, not without
+    A, b, B = fx.matrix("elastic"), fx.array("elastic_b"), fx.array("elastic_B")
+    ml = amg.smoothed_aggregation(A, B=B)
+    x, res = amg._solve(ml, b, log=True, reltol=1e-10)
+    xr, resr = oracle.OracleHierarchy(ml).solve(b, log=True, reltol=1e-10)
+    assert len(res) == len(resr) and np.linalg.norm(x - xr) <= TOL_SOLVE_X * np.linalg.norm(xr)
+    assert np.linalg.norm(A.matvec(x) - b) <= np.sqrt(np.finfo(float).eps) * np.linalg.norm(b)     # Julia's `≈`
+    xc = amg.cg(A, b, Pl=amg.aspreconditioner(ml), reltol=1e-10)
+    assert np.linalg.norm(A.matvec(xc) - b) <= 1e-9 * np.linalg.norm(b)
+    ml2 = amg.smoothed_aggregation(A, coarse_solver=amg.Pinv)
+    x2, res2 = amg._solve(ml2, b, log=True, reltol=1e-10)
+    assert not np.linalg.norm(A.matvec(x2) - b) <= np.sqrt(np.finfo(float).eps) * np.linalg.norm(b)
+    assert res2[0] > res2[-1]
+
+
+def test_regression_95_nonsymmetric_device(amg, fx):
+    # test/test_regression.jl:71-83
+    N = 10000
+    A = fx.sprand_plus_diag(N, 0.001, 5.0, seed=5)
+    b = np.ones(N)
+    for f in (amg.ruge_stuben, amg.smoothed_aggregation):
+        ml = f(A, symmetry=amg.NoSymmetry())
+        x = amg._solve(ml, b)
+        assert np.allclose(A.matvec(x), b, rtol=1e-8)
+        xr = oracle.OracleHierarchy(ml).solve(b)
+        assert np.linalg.norm(x - xr) <= TOL_SOLVE_X * np.linalg.norm(xr)
+        ml.release()
+
+
+def test_no_level_hierarchy_and_quirks(amg):
+    # test/test_regression.jl:41-57 + SURVEY appendix C
+    for n in (1, 3, 10):
+        A = amg.poisson(n)
+        ml = amg.ruge_stuben(A)
+        assert len(ml) == 1
+        b = A.matvec(np.ones(n))
+        assert np.allclose(amg._solve(ml, b), np.ones(n))
+    A = amg.poisson(100)
+    ml = amg.ruge_stuben(A)
+    x = np.ones(100)
+    x, res = amg._solve_(x, ml, np.zeros(100), log=True)
+    assert np.array_equal(x, np.ones(100)) and list(res) == [0.0]          # ||b|| = 0: loop never runs
+    before = ml.device().launch_count()
+    amg._solve(ml, np.ones(100), maxiter=3, calculate_residual=False)
+    assert ml.device().launch_count() > before
+    x32 = amg._solve(ml, np.ones(100, dtype=np.float32))
+    assert x32.dtype == np.float64                                           # promote(eltype(A), eltype(b)) runtests.jl:244-259
+
+
+# ---- larger sizes: properties that need no oracle run -------------------------------------------
+def test_properties_at_size(amg, jac):
+    A = amg.poisson((96, 96, 96))
+    n = A.n
+    ml = amg.ruge_stuben(A)
+    dev = ml.device()
+    r = _rng(12)
+    x, y = r.standard_normal(n), r.standard_normal(n)
+    # linearity of the SpMV and agreement with the closed-form stencil
+    ax, ay, axy = dev.apply(0, 0, np.empty(n), x), dev.apply(0, 0, np.empty(n), y), dev.apply(0, 0, np.empty(n), 2 * x - 3 * y)
+    assert relinf(axy, 2 * ax - 3 * ay) <= 1e-12
+    X = x.reshape(96, 96, 96)
+    st = 6 * X.copy()
+    for ax_ in range(3):
+        sl_lo = [slice(None)] * 3
+        sl_hi = [slice(None)] * 3
+        sl_lo[ax_], sl_hi[ax_] = slice(0, -1), slice(1, None)
+        st[tuple(sl_hi)] -= X[tuple(sl_lo)]
+        st[tuple(sl_lo)] -= X[tuple(sl_hi)]
+    assert relinf(ax, st.reshape(-1)) <= TOL_KERNEL
+    # A*ones has the known solution ones; the solve converges to it; history is monotone
+    b = A.matvec(np.ones(n))
+    xs, hist = amg._solve(ml, b, log=True)
+    assert hist[-1] <= np.sqrt(np.finfo(float).eps) * hist[0] and np.all(np.diff(hist) < 0)
+    assert np.abs(xs - 1).max() < 1e-6
+    # R = P' : <R r, e> == <r, P e>
+    lv = ml.levels[0]
+    e = r.standard_normal(lv.R.shape[0])
+    Rr, Pe = dev.apply(0, 2, np.empty(lv.R.shape[0]), x), dev.apply(0, 1, np.empty(n), e)
+    assert abs(Rr @ e - x @ Pe) <= 1e-10 * abs(x @ Pe)
+    # a converged x is a fixed point of every smoother up to the residual
+    xx = xs.copy()
+    dev.smooth(0, 0, xx, b)
+    assert np.abs(xx - xs).max() < 1e-6
+    ml.release()
