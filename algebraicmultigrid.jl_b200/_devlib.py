@@ -28,7 +28,8 @@ SYMBOLS = [
     "b200amg_cycle", "b200amg_precond", "b200amg_smooth", "b200amg_apply", "b200amg_residual",
     "b200amg_coarse_solve", "b200amg_norm", "b200amg_pcg", "b200amg_smoother_create", "b200amg_smoother_apply",
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
-    "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors",
+    "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
+    "b200amg_residual_timings", "b200amg_get_stream",
 ]
 
 
@@ -98,6 +99,9 @@ def lib():
             "b200amg_time_kernel": [vp, i32, i32, i32, i32, i32, C.POINTER(dbl)],
             "b200amg_profile_cycle": [vp, i32, vp, i32],
             "b200amg_device_vectors": [vp, C.POINTER(vp), C.POINTER(vp)],
+            "b200amg_set_option": [vp, i32, dbl],
+            "b200amg_residual_timings": [vp, vp, i32, C.POINTER(i32)],
+            "b200amg_get_stream": [vp, C.POINTER(vp)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -280,6 +284,20 @@ class DeviceHierarchy:
         ms = np.zeros(cap)
         _check(lib().b200amg_profile_cycle(self._h, cycle, _ptr(ms), cap))
         return ms.reshape(self.nlevels, 6)
+
+    def set_option(self, option, value):
+        _check(lib().b200amg_set_option(self._h, int(option), float(value)))
+
+    def residual_timings(self, cap=4096):
+        ms = np.zeros(cap)
+        n = C.c_int32(0)
+        _check(lib().b200amg_residual_timings(self._h, _ptr(ms), cap, C.byref(n)))
+        return ms[: n.value].copy()
+
+    def stream(self):
+        s = C.c_void_p()
+        _check(lib().b200amg_get_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     def device_vectors(self):
         x, b = C.c_void_p(), C.c_void_p()

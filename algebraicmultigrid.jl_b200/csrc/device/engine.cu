@@ -374,6 +374,10 @@ struct b200amg_hierarchy {
   // profiling
   bool profiling = false;
   std::vector<double>* prof_ms = nullptr;
+  // per-iteration timing of the fine-level convergence residual (B200AMG_OPT_TIME_RESIDUAL)
+  bool time_residual = false;
+  std::vector<cudaEvent_t> res_events;   // 2 per iteration
+  int res_events_used = 0;
 };
 typedef b200amg_hierarchy H;
 
@@ -618,7 +622,13 @@ static void run_cycle(H* h, int cycle) {
 static void residual_norm(H* h) {
   const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
   double* res = h->levels.empty() ? h->res_final : h->levels[0]->res;
+  const bool timed = h->time_residual && h->res_events_used + 2 <= (int)h->res_events.size();
+  if (timed) CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used], h->stream));
   residual(h, A, h->x0, h->b0, res);
+  if (timed) {
+    CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used + 1], h->stream));
+    h->res_events_used += 2;
+  }
   norm2_async(h, h->n0, res, h->scalars);
 }
 
@@ -769,6 +779,7 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
   cudaFree(h->partial); cudaFree(h->scalars); cudaFreeHost(h->h_scalars);
   cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush);
+  for (cudaEvent_t e : h->res_events) cudaEventDestroy(e);
   for (int c = 0; c < 3; ++c)
     if (h->cycle_graph[c]) cudaGraphExecDestroy(h->cycle_graph[c]);
   if (h->resnorm_graph) cudaGraphExecDestroy(h->resnorm_graph);
@@ -789,6 +800,15 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
   to_dev(h, h->b0, b, n, memkind);
   to_dev(h, h->x0, x, n, memkind);
   int nr = 0;
+  h->res_events_used = 0;
+  if (h->time_residual) {
+    const size_t want = 2 * (size_t)std::min(std::max(maxiter, 0), 2048);
+    while (h->res_events.size() < want) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreate(&e));
+      h->res_events.push_back(e);
+    }
+  }
   norm2_async(h, n, h->b0, h->scalars);
   double normb = read_scalar(h, h->scalars), normres = normb;                        // :170
   if (normb != 0) abstol = std::max(reltol * normb, abstol);                           // :171-173
@@ -1117,6 +1137,39 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
   h->profiling = false;
   h->prof_ms = nullptr;
   for (int i = 0; i < cap; ++i) ms[i] = acc[i];
+  API_END
+}
+
+int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
+  API_BEGIN
+  REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  switch (option) {
+    case B200AMG_OPT_USE_GRAPHS: h->use_graphs = value != 0.0; break;
+    case B200AMG_OPT_TIME_RESIDUAL: h->time_residual = value != 0.0; break;
+    default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown option %d", option);
+  }
+  API_END
+}
+
+int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n) {
+  API_BEGIN
+  REQUIRE(h && ms && n, B200AMG_ERR_BAD_ARG, "null argument");
+  set_device(h);
+  int k = 0;
+  for (int i = 0; i + 1 < h->res_events_used && k < cap; i += 2, ++k) {
+    float t = 0;
+    CUDA_OK(cudaEventSynchronize(h->res_events[i + 1]));
+    CUDA_OK(cudaEventElapsedTime(&t, h->res_events[i], h->res_events[i + 1]));
+    ms[k] = t;
+  }
+  *n = k;
+  API_END
+}
+
+int32_t b200amg_get_stream(b200amg_handle_t h, void** stream) {
+  API_BEGIN
+  REQUIRE(h && stream, B200AMG_ERR_BAD_ARG, "null argument");
+  *stream = (void*)h->stream;
   API_END
 }
 

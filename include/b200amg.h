@@ -180,6 +180,15 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
  * Runs one un-captured cycle with an event pair around every phase; ms[level*6 + phase]
  * accumulates (cap >= 6*length). */
 int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int32_t cap);
+/* Engine options (before or after finalize).  USE_GRAPHS (default 1): replay each cycle type as a
+ * captured CUDA graph.  TIME_RESIDUAL (default 0): b200amg_solve brackets the fine-level
+ * convergence-residual kernel (multilevel.jl:188-189) of every iteration with a CUDA event pair on
+ * the launching stream; read the per-iteration milliseconds back with b200amg_residual_timings. */
+enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1 };
+int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
+int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
+/* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
+int32_t b200amg_get_stream(b200amg_handle_t h, void** stream);
 /* raw device pointers of the level-0 work vectors (x, b) for zero-copy callers (torch / CUDA.jl) */
 int32_t b200amg_device_vectors(b200amg_handle_t h, double** x, double** b);
 
