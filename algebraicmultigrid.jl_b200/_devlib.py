@@ -29,7 +29,7 @@ SYMBOLS = [
     "b200amg_coarse_solve", "b200amg_norm", "b200amg_pcg", "b200amg_smoother_create", "b200amg_smoother_apply",
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
-    "b200amg_residual_timings", "b200amg_get_stream",
+    "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline",
 ]
 
 
@@ -102,6 +102,7 @@ def lib():
             "b200amg_set_option": [vp, i32, dbl],
             "b200amg_residual_timings": [vp, vp, i32, C.POINTER(i32)],
             "b200amg_get_stream": [vp, C.POINTER(vp)],
+            "b200amg_debug_gs_timeline": [vp, i32, i32, vp, i64, C.POINTER(i64)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -293,6 +294,13 @@ class DeviceHierarchy:
         n = C.c_int32(0)
         _check(lib().b200amg_residual_timings(self._h, _ptr(ms), cap, C.byref(n)))
         return ms[: n.value].copy()
+
+    def gs_timeline(self, level, backward=False):
+        cap = 8 * (self.level_info(level)["n"] + 8)
+        out = np.zeros(cap, dtype=np.uint64)
+        nt = C.c_int64(0)
+        _check(lib().b200amg_debug_gs_timeline(self._h, level, int(backward), _ptr(out), cap, C.byref(nt)))
+        return out[: 8 * nt.value].reshape(-1, 8).astype(np.int64)
 
     def stream(self):
         s = C.c_void_p()

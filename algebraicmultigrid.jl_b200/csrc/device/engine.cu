@@ -18,6 +18,7 @@
 
 #include "b200amg.h"
 #include "kernels.cuh"
+#include "stream.cuh"
 
 using namespace b200amg;
 
@@ -207,27 +208,61 @@ static T* dev_upload(const std::vector<T>& v, int64_t pad = 0) {
   return p;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
 struct DevCsr {
   int64_t nrows = 0, ncols = 0, nnz = 0;
   int* ptr = nullptr;
   int* idx = nullptr;
   double* val = nullptr;
   int lanes = 8;  // lanes per row of the vector kernels
+  // tile plan of the TMA stream kernels (stream.cuh); ntiles == 0: not streamable (a row > kTileNnz)
+  int4* meta = nullptr;
+  int ntiles = 0;
+  int stream_lanes = 1;
   bool owner = false;
   void upload(const HostCsr& h) {
     nrows = h.nrows; ncols = h.ncols; nnz = h.nnz();
-    ptr = dev_upload(h.ptr);
+    ptr = dev_upload(h.ptr, 8);
     idx = dev_upload(h.idx, 8);
     val = dev_upload(h.val, 8);
     owner = true;
     const double mean = nrows ? (double)nnz / (double)nrows : 0.0;
     lanes = 2;
     while (lanes < 32 && lanes < mean) lanes *= 2;
+    plan_tiles(h, mean);
+  }
+  void plan_tiles(const HostCsr& h, double mean) {
+    ntiles = 0;
+    if (nrows == 0 || env_int("B200AMG_NO_STREAM", 0)) return;
+    stream_lanes = 1;
+    while (stream_lanes < 32 && mean > 12.0 * stream_lanes) stream_lanes *= 2;
+    stream_lanes = env_int("B200AMG_STREAM_LANES", stream_lanes);
+    const int G = kStreamThreads / stream_lanes;
+    int passes = (int)(kTileNnz / std::max(1.0, G * std::max(mean, 1.0)));
+    passes = std::min(std::max(passes, 1), 4);
+    const int rows_per_tile = std::min(G * passes, kTileRowsMax);
+    std::vector<int4> m;
+    m.reserve((size_t)(nnz / kTileNnz + nrows / rows_per_tile + 2));
+    int64_t r = 0;
+    while (r < nrows) {
+      int64_t e = r;
+      const int k0 = h.ptr[r];
+      while (e < nrows && e - r < rows_per_tile && h.ptr[e + 1] - k0 <= kTileNnz) ++e;
+      if (e == r) return;  // a single row exceeds the tile: leave ntiles = 0 (vector kernels take over)
+      m.push_back(make_int4((int)r, (int)e, k0, h.ptr[e]));
+      r = e;
+    }
+    meta = dev_upload(m);
+    ntiles = (int)m.size();
   }
   void alias(const DevCsr& o) { *this = o; owner = false; }
   void release() {
-    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); }
-    ptr = idx = nullptr; val = nullptr; owner = false;
+    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(meta); }
+    ptr = idx = nullptr; val = nullptr; meta = nullptr; ntiles = 0; owner = false;
   }
 };
 
@@ -238,12 +273,19 @@ struct SweepItem {
 struct DevSchedule {
   int nlev = 0;
   int64_t n = 0;
-  int* rows = nullptr;
+  int* rows = nullptr;     // rows in schedule order (the permutation of the dataflow sweep)
   int* lvlptr = nullptr;
   std::vector<int> h_lvlptr;
   std::vector<SweepItem> items;
   bool built = false;
-  void upload(const HostSchedule& h, int lanes) {
+  // dataflow sweep (stream.cuh: gs_dataflow_kernel): the walked matrix once more, rows in schedule order
+  int df_lanes = 1, df_threads = 128, ntasks = 0;
+  int4* tasks = nullptr;
+  int* wave_ntasks = nullptr;
+  unsigned* counters = nullptr;   // [0] ticket, [1 + w] finished tasks of wavefront w
+  int *pptr = nullptr, *pcol = nullptr;
+  double* pval = nullptr;
+  void upload(const HostSchedule& h, const HostCsr& w, int lanes) {
     nlev = (int)h.lvlptr.size() - 1;
     n = (int64_t)h.rows.size();
     rows = dev_upload(h.rows);
@@ -264,9 +306,44 @@ struct DevSchedule {
         ++l;
       }
     }
+    // ---- dataflow layout ----
+    const double mean = n ? (double)w.nnz() / (double)n : 0.0;
+    df_lanes = 1;
+    while (df_lanes < 32 && kGsPrefetch * df_lanes < (mean <= kGsPrefetch ? mean : 1.25 * mean)) df_lanes *= 2;
+    df_lanes = env_int("B200AMG_GS_LANES", df_lanes);
+    df_threads = env_int("B200AMG_GS_THREADS", 128) == 256 ? 256 : 128;
+    const int R = df_threads / df_lanes;
+    std::vector<int4> tk;
+    std::vector<int> wn(std::max(nlev, 1), 0);
+    for (int lv = 0; lv < nlev; ++lv)
+      for (int p = h_lvlptr[lv]; p < h_lvlptr[lv + 1]; p += R) {
+        tk.push_back(make_int4(p, std::min(R, h_lvlptr[lv + 1] - p), lv, 0));
+        wn[lv]++;
+      }
+    for (int4& t : tk) t.w = t.z > 0 ? wn[t.z - 1] : 0;
+    std::vector<int> pp(n + 1, 0), pc((size_t)w.nnz());
+    std::vector<double> pv((size_t)w.nnz());
+    for (int64_t p = 0; p < n; ++p) pp[p + 1] = pp[p] + (w.ptr[h.rows[p] + 1] - w.ptr[h.rows[p]]);
+    for (int64_t p = 0; p < n; ++p) {
+      const int r = h.rows[p];
+      std::copy(w.idx.begin() + w.ptr[r], w.idx.begin() + w.ptr[r + 1], pc.begin() + pp[p]);
+      std::copy(w.val.begin() + w.ptr[r], w.val.begin() + w.ptr[r + 1], pv.begin() + pp[p]);
+    }
+    ntasks = (int)tk.size();
+    tasks = dev_upload(tk);
+    wave_ntasks = dev_upload(wn);
+    counters = dev_alloc<unsigned>((int64_t)(nlev + 2) * kGsCounterStride);
+    pptr = dev_upload(pp);
+    pcol = dev_upload(pc, 8);
+    pval = dev_upload(pv, 8);
     built = true;
   }
-  void release() { cudaFree(rows); cudaFree(lvlptr); rows = lvlptr = nullptr; built = false; }
+  void release() {
+    cudaFree(rows); cudaFree(lvlptr); cudaFree(tasks); cudaFree(wave_ntasks); cudaFree(counters);
+    cudaFree(pptr); cudaFree(pcol); cudaFree(pval);
+    rows = lvlptr = nullptr; tasks = nullptr; wave_ntasks = nullptr; counters = nullptr; pptr = pcol = nullptr; pval = nullptr;
+    built = false;
+  }
 };
 
 struct SmootherCfg {
@@ -316,8 +393,8 @@ struct SmootherMatrix {
       for (int64_t i = 0; i < n; ++i)
         REQUIRE(d[i] != 0.0, B200AMG_ERR_SINGULAR, "SingularException(%lld)", (long long)(i + 1));
     }
-    if (need_fwd) fwd.upload(build_schedule(w, wt, true), walked().lanes);
-    if (need_bwd) bwd.upload(build_schedule(w, wt, false), walked().lanes);
+    if (need_fwd) fwd.upload(build_schedule(w, wt, true), w, walked().lanes);
+    if (need_bwd) bwd.upload(build_schedule(w, wt, false), w, walked().lanes);
   }
   void release() {
     A.release(); At.release(); fwd.release(); bwd.release();
@@ -364,6 +441,11 @@ struct b200amg_hierarchy {
   int64_t cycle_graph_launches[3] = {0, 0, 0};
   cudaGraphExec_t resnorm_graph = nullptr;
   bool use_graphs = true;
+  int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
+  int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
+  int gs_acquire = 0;     // consumer-side acquire of the dataflow sweep: 0 none (see stream.cuh), 1 ld.acquire, 2 fence
+  unsigned long long* gs_debug = nullptr;   // 8 timestamps per task of the last dataflow sweep (diagnostics)
+  int gs_mode = 1;        // 1: persistent dataflow sweep, 0: one launch per wavefront (fallback / A-B)
   bool finalized = false;
   bool capturing = false;
   int64_t launches = 0;       // kernels launched (graph replays add their node counts)
@@ -391,9 +473,43 @@ static inline unsigned grid_for(int64_t work_items) {
 // ------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------
+// ---- TMA stream kernels ---------------------------------------------------------------------
+template <int T, int MODE>
+static void stream_set_attr() {
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+}
+template <int MODE>
+static void stream_set_attr_all() {
+  stream_set_attr<1, MODE>(); stream_set_attr<2, MODE>(); stream_set_attr<4, MODE>();
+  stream_set_attr<8, MODE>(); stream_set_attr<16, MODE>(); stream_set_attr<32, MODE>();
+}
+static void stream_kernels_init() {   // once per device context: opt in to 86 KB of dynamic shared memory
+  stream_set_attr_all<0>(); stream_set_attr_all<1>(); stream_set_attr_all<2>(); stream_set_attr_all<3>(); stream_set_attr_all<4>();
+}
+template <int MODE>
+static void launch_stream(H* h, const DevCsr& A, const double* x, const double* b, double* y, double omega,
+                          const double* diagvals) {
+  const int ctas = std::min(A.ntiles, kNumSM * 2);
+  int chunk = h->stream_chunk > 0 ? h->stream_chunk : (A.ntiles + ctas - 1) / ctas;
+#define B200AMG_STREAM_CASE(TT)                                                                                         \
+  case TT:                                                                                                              \
+    csr_stream_kernel<TT, MODE><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, \
+                                                                                      A.val, x, b, y, omega, diagvals); \
+    break;
+  switch (A.stream_lanes) {
+    B200AMG_STREAM_CASE(1) B200AMG_STREAM_CASE(2) B200AMG_STREAM_CASE(4) B200AMG_STREAM_CASE(8) B200AMG_STREAM_CASE(16)
+    default:
+      csr_stream_kernel<32, MODE><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx,
+                                                                                        A.val, x, b, y, omega, diagvals);
+  }
+#undef B200AMG_STREAM_CASE
+  count_launch(h);
+}
+
 template <int MODE>
 static void launch_csr(H* h, const DevCsr& A, const double* x, const double* b, double* y) {
   if (A.nrows == 0) return;
+  if (A.ntiles > 0) { launch_stream<MODE>(h, A, x, b, y, 0.0, nullptr); return; }
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: csr_vec_kernel<2, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
@@ -409,6 +525,7 @@ static void residual(H* h, const DevCsr& A, const double* x, const double* b, do
 static void spmv_add(H* h, const DevCsr& A, const double* x, double* y) { launch_csr<2>(h, A, x, nullptr, y); }
 
 static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const double* b, double* xout, double w) {
+  if (A.ntiles > 0) { launch_stream<3>(h, A, xin, b, xout, w, nullptr); return; }
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: jacobi_fast_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
@@ -421,6 +538,7 @@ static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const d
 }
 static void launch_jacobi_general(H* h, const DevCsr& A, const double* diag, const double* xin, const double* b,
                                   double* xout, double w) {
+  if (A.ntiles > 0) { launch_stream<4>(h, A, xin, b, xout, w, diag); return; }
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: jacobi_general_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
@@ -446,7 +564,41 @@ static void launch_sweep_T(H* h, const DevCsr& A, const DevSchedule& sc, double*
     count_launch(h);
   }
 }
+template <int T, int BS>
+static int gs_dataflow_ctas() {   // co-resident CTAs of the persistent dataflow sweep
+  static int cached = 0;
+  if (!cached) {
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_kernel<T, BS>, BS, 0));
+    cached = std::max(1, per_sm) * kNumSM;
+  }
+  return cached;
+}
+template <int T, int BS>
+static void launch_dataflow_T(H* h, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS>());
+  CUDA_OK(cudaMemsetAsync(sc.counters, 0, sizeof(unsigned) * (size_t)(sc.nlev + 2) * kGsCounterStride, h->stream));
+  gs_dataflow_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.wave_ntasks, sc.counters, sc.rows, sc.pptr, sc.pcol,
+                                                       sc.pval, x, b, w, sor, h->gs_acquire, h->opaque_zero, h->gs_debug);
+  count_launch(h);
+}
+static void launch_dataflow(H* h, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  if (sc.ntasks == 0) return;
+#define B200AMG_DF_CASE(TT)                                                    \
+  case TT:                                                                     \
+    if (sc.df_threads == 128) launch_dataflow_T<TT, 128>(h, sc, x, b, w, sor); \
+    else launch_dataflow_T<TT, 256>(h, sc, x, b, w, sor);                      \
+    break;
+  switch (sc.df_lanes) {
+    B200AMG_DF_CASE(1) B200AMG_DF_CASE(2) B200AMG_DF_CASE(4) B200AMG_DF_CASE(8) B200AMG_DF_CASE(16)
+    default:
+      if (sc.df_threads == 128) launch_dataflow_T<32, 128>(h, sc, x, b, w, sor);
+      else launch_dataflow_T<32, 256>(h, sc, x, b, w, sor);
+  }
+#undef B200AMG_DF_CASE
+}
 static void launch_sweep(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  if (h->gs_mode == 1) { launch_dataflow(h, sc, x, b, w, sor); return; }
   switch (A.lanes) {
     case 2: launch_sweep_T<2>(h, A, sc, x, b, w, sor); break;
     case 4: launch_sweep_T<4>(h, A, sc, x, b, w, sor); break;
@@ -573,8 +725,8 @@ static int64_t estimate_launches(H* h, int cycle, int lvl) {
     if (c.kind == 0) return 0;
     if (c.kind == B200AMG_SMOOTHER_JACOBI) return c.iter + 1;
     int64_t per = 0;
-    if (c.sweep == 1 || c.sweep == 3) per += (int64_t)L.M.fwd.items.size();
-    if (c.sweep == 2 || c.sweep == 3) per += (int64_t)L.M.bwd.items.size();
+    if (c.sweep == 1 || c.sweep == 3) per += h->gs_mode == 1 ? 1 : (int64_t)L.M.fwd.items.size();
+    if (c.sweep == 2 || c.sweep == 3) per += h->gs_mode == 1 ? 1 : (int64_t)L.M.bwd.items.size();
     return per * c.iter;
   };
   int64_t n = sm(L.pre) + sm(L.post) + 4;
@@ -679,6 +831,10 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->device = device;
   CUDA_OK(cudaSetDevice(device));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  stream_kernels_init();
+  h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
+  h->gs_mode = env_int("B200AMG_GS_MODE", 1);
+  h->gs_acquire = env_int("B200AMG_GS_ACQUIRE", 0);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
   CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * 16));
@@ -1146,6 +1302,9 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
   switch (option) {
     case B200AMG_OPT_USE_GRAPHS: h->use_graphs = value != 0.0; break;
     case B200AMG_OPT_TIME_RESIDUAL: h->time_residual = value != 0.0; break;
+    case B200AMG_OPT_STREAM_CHUNK: h->stream_chunk = (int)value; break;
+    case B200AMG_OPT_GS_MODE: h->gs_mode = (int)value; break;
+    case B200AMG_OPT_GS_ACQUIRE: h->gs_acquire = (int)value; break;
     default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown option %d", option);
   }
   API_END
@@ -1163,6 +1322,31 @@ int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, in
     ms[k] = t;
   }
   *n = k;
+  API_END
+}
+
+int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t backward, uint64_t* out, int64_t cap,
+                                  int64_t* ntasks) {
+  API_BEGIN
+  check_ready(h);
+  REQUIRE(level >= 0 && level < (int)h->levels.size() && out && ntasks, B200AMG_ERR_BAD_ARG, "bad argument");
+  Level& L = *h->levels[level];
+  const DevSchedule& sc = backward ? L.M.bwd : L.M.fwd;
+  REQUIRE(sc.built, B200AMG_ERR_STATE, "no Gauss-Seidel schedule on this level");
+  const int64_t words = (int64_t)sc.ntasks * 8;
+  REQUIRE(cap >= words, B200AMG_ERR_BAD_ARG, "timeline buffer too small (%lld needed)", (long long)words);
+  unsigned long long* d = dev_alloc<unsigned long long>(words);
+  CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)words, h->stream));
+  h->gs_debug = d;
+  const int sor = L.pre.kind == B200AMG_SMOOTHER_SOR;
+  double* x = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
+  const double* b = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
+  launch_dataflow(h, sc, x, b, L.pre.omega, sor);
+  h->gs_debug = nullptr;
+  CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(d);
+  *ntasks = sc.ntasks;
   API_END
 }
 

@@ -1,0 +1,367 @@
+// CSR "stream" kernels: the bandwidth path of the solve phase on sm_100a.
+//
+// The matrix streams (values, column indices, row pointers) are perfectly contiguous, so they are
+// moved HBM -> shared memory by the TMA unit as 1-D bulk copies (cp.async.bulk, SASS UBLKCP)
+// signalled on an mbarrier, three stages deep, by persistent CTAs; the threads only wait on the
+// barrier, gather x through L1/L2 and reduce rows out of shared memory.  Nothing about the matrix
+// ever occupies a register while it is in flight, which is what lets two CTAs per SM keep
+// > 100 KB of HBM requests outstanding (Little's law needs ~31 KB per SM at 7.7 TB/s).
+//
+// A matrix is cut at upload into TILES of whole rows (<= kTileNnz non-zeros, <= rows_per_tile rows);
+// tile t is described by one int4 {first row, end row, first nnz, end nnz}.  T lanes cooperate on
+// a row (T = 1 for stencil-like matrices: one thread per row, sequential ascending-column
+// accumulation with separate multiply and add roundings == the accumulation order of the
+// reference's CSC scatter `y[rowval[k]] += nzval[k]*x[j]`, so T = 1 results are bit-identical to
+// the CPU oracle; T > 1 differs by summation order only).
+//
+//   MODE 0  y  = A x                       mul!(res, A, x)                multilevel.jl:188,219,223
+//   MODE 1  y  = b - A x                   res .= b .- res (fused)        multilevel.jl:189,220
+//   MODE 2  y += A x                       mul!(res,P,cx); x .+= res      multilevel.jl:233-234
+//   MODE 3  y  = jacobi_fast(x)            smooth!(::FastJacobiSmoother)  smoother.jl:113-141
+//   MODE 4  y  = jacobi_general(x)         smooth!(::JacobiSmoother)      smoother.jl:157-171
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200amg {
+
+constexpr int kStreamThreads = 256;
+constexpr int kTileNnz = 2048;
+constexpr int kTileRowsMax = 1024;
+constexpr int kStages = 3;
+
+struct __align__(16) StreamStage {
+  double val[kTileNnz + 8];
+  int col[kTileNnz + 8];
+  int rp[kTileRowsMax + 8];
+};
+static_assert(sizeof(StreamStage) % 16 == 0, "stage must keep 16-byte alignment");
+constexpr int kStreamSmemBytes = kStages * (int)sizeof(StreamStage);
+
+// ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk copy global -> shared, completion counted in bytes on `bar` (TMA unit; SASS UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void stream_issue(StreamStage& S, uint64_t* bar, const int4 m, const int* __restrict__ rowptr,
+                                             const int* __restrict__ col, const double* __restrict__ val) {
+  const int ka = m.z & ~3, kcnt = (m.w - ka + 3) & ~3;
+  const int ra = m.x & ~3, rcnt = (m.y + 1 - ra + 3) & ~3;
+  mbar_expect_tx(bar, (uint32_t)(kcnt * 12 + rcnt * 4));
+  if (kcnt) {
+    bulk_g2s(S.val, val + ka, (uint32_t)kcnt * 8u, bar);
+    bulk_g2s(S.col, col + ka, (uint32_t)kcnt * 4u, bar);
+  }
+  bulk_g2s(S.rp, rowptr + ra, (uint32_t)rcnt * 4u, bar);
+}
+
+template <int T>
+__device__ __forceinline__ double lanes_sum(double v) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o, T);
+  return v;
+}
+
+// tiles are handed out in runs of `chunk` consecutive tiles per CTA (chunk = 1: round robin)
+__device__ __forceinline__ int stream_tile_of(int i, int chunk) {
+  return (i / chunk) * ((int)gridDim.x * chunk) + (int)blockIdx.x * chunk + (i % chunk);
+}
+
+template <int T, int MODE>
+__global__ void __launch_bounds__(kStreamThreads, 2)
+    csr_stream_kernel(int ntiles, int chunk, const int4* __restrict__ meta, const int* __restrict__ rowptr,
+                      const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                      const double* __restrict__ b, double* __restrict__ y, double omega,
+                      const double* __restrict__ diagvals) {
+  extern __shared__ __align__(128) unsigned char stream_smem[];
+  StreamStage* st = reinterpret_cast<StreamStage*>(stream_smem);
+  __shared__ __align__(8) uint64_t full[kStages];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const int t = stream_tile_of(s, chunk);
+      if (t < ntiles) stream_issue(st[s], &full[s], __ldg(meta + t), rowptr, col, val);
+    }
+  }
+  constexpr int G = kStreamThreads / T;   // rows relaxed per pass
+  const int g = tid / T, lane = tid % T;
+  int s = 0;
+  uint32_t parity = 0;
+  // the CTA's tiles are a prefix-closed sequence: stop at the first index beyond the matrix
+  for (int i = 0;; ++i) {
+    const int t = stream_tile_of(i, chunk);
+    if (t >= ntiles) {
+      // with chunk > 1 a later run can still hold valid tiles only if this one did: runs are
+      // ordered, so the first invalid tile ends the CTA's work.
+      break;
+    }
+    const int4 m = __ldg(meta + t);
+    const int nrows = m.y - m.x, ka = m.z & ~3, rofs = m.x - (m.x & ~3);
+    // operands of the epilogue of the first pass: requested before the barrier wait
+    double pre_b = 0.0, pre_x = 0.0, pre_d = 0.0;
+    if (lane == 0 && g < nrows) {
+      const int row = m.x + g;
+      if (MODE == 1 || MODE == 3 || MODE == 4) pre_b = __ldg(b + row);
+      if (MODE == 2) pre_x = y[row];
+      if (MODE == 3 || MODE == 4) pre_x = __ldg(x + row);
+      if (MODE == 4) pre_d = __ldg(diagvals + row);
+    }
+    mbar_wait(&full[s], parity);
+    const StreamStage& S = st[s];
+    for (int rbase = 0; rbase < nrows; rbase += G) {
+      const int r = rbase + g;
+      double sum = 0.0, diag = 0.0;
+      if (r < nrows) {
+        const int ks = S.rp[rofs + r] - ka, ke = S.rp[rofs + r + 1] - ka;
+        const int row = m.x + r;
+#pragma unroll 4
+        for (int k = ks + lane; k < ke; k += T) {
+          const int c = S.col[k];
+          const double v = S.val[k];
+          if (MODE == 3) {
+            if (c == row) diag = v;
+            else sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+          } else {
+            sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+          }
+        }
+      }
+      if (T > 1) {
+        sum = lanes_sum<T>(sum);
+        if (MODE == 3) diag = lanes_sum<T>(diag);
+      }
+      if (lane == 0 && r < nrows) {
+        const int row = m.x + r;
+        double bv = pre_b, xv = pre_x, dv = pre_d;
+        if (rbase != 0) {
+          if (MODE == 1 || MODE == 3 || MODE == 4) bv = __ldg(b + row);
+          if (MODE == 2) xv = y[row];
+          if (MODE == 3 || MODE == 4) xv = __ldg(x + row);
+          if (MODE == 4) dv = __ldg(diagvals + row);
+        }
+        if (MODE == 0) y[row] = sum;
+        else if (MODE == 1) y[row] = bv - sum;
+        else if (MODE == 2) y[row] = xv + sum;
+        else if (MODE == 3)   // (one - ω) * temp[i] + ω * ((b[i] - rsum) / diag), no FMA contraction
+          y[row] = (diag == 0.0) ? xv
+                                 : __dadd_rn(__dmul_rn(1.0 - omega, xv), __dmul_rn(omega, __ddiv_rn(__dsub_rn(bv, sum), diag)));
+        else                  // x[i] -= ω * temp[i] / d   with temp = A x - b
+          y[row] = (dv != 0.0) ? __dsub_rn(xv, __ddiv_rn(__dmul_rn(omega, __dsub_rn(sum, bv)), dv)) : xv;
+      }
+    }
+    __syncthreads();   // every thread is done with stage s
+    if (tid == 0) {
+      const int tn = stream_tile_of(i + kStages, chunk);
+      if (tn < ntiles) stream_issue(st[s], &full[s], __ldg(meta + tn), rowptr, col, val);
+    }
+    if (++s == kStages) { s = 0; parity ^= 1u; }
+  }
+}
+
+
+
+// =============================================================================================
+// Gauss-Seidel / SOR as a DATAFLOW sweep (exact lexicographic semantics of gs! smoother.jl:73-90 and
+// sor_step! :205-221).
+//
+// The rows are stored a second time in wavefront order (level schedule of the symmetrised
+// pattern: rows of one wavefront are mutually independent; every earlier-ordered neighbour sits in
+// an earlier wavefront, every later-ordered one in a later wavefront).  The sweep is ONE persistent
+// kernel: CTAs claim TASKS (<= 256/T consecutive rows of one wavefront) in schedule order from a
+// ticket counter, prefetch everything that does not depend on x (row pointers, column indices,
+// values, b) into registers, and only then wait until the previous wavefront's completion counter
+// is full (one acquire-poll per CTA), gather x through L2 (ld.cg: other SMs wrote it), relax and
+// publish with a release-increment of their own wavefront's counter.  Dependency latency per
+// wavefront is one L2 round trip instead of a kernel launch or a grid barrier, and the matrix
+// streams of later wavefronts are already in flight while earlier ones resolve.
+//
+// Claiming by ticket makes it deadlock-free for any grid size: a task is only ever held by a
+// resident CTA, and the lowest unfinished task never waits on anything unfinished.
+//
+// T = 1: one thread per row, sequential ascending-column accumulation, separate multiply/add
+// roundings and a true division -> bit-identical to the reference's sequential sweep.
+// =============================================================================================
+constexpr int kGsThreads = 256;
+constexpr int kGsPrefetch = 8;   // (column, value) pairs a lane holds in registers across the wait
+
+constexpr int kGsCounterStride = 64;   // uints between counters: 256 B apart = different L2 slices, no hot line
+
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ double g_gs_zero = 0.0;   // what padding slots of the gather burst read
+constexpr int kGsFarWaves = 4;   // CTAs this many wavefronts ahead of the front sleep-poll
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_relaxed_inc(unsigned* p) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+// tasks[t] = {first position in schedule order, rows, wavefront, tasks of the previous wavefront}
+// counters[0] = ticket, counters[(1 + w) * kGsCounterStride] = finished tasks of wavefront w (zeroed before the launch)
+template <int T, int BS>
+__global__ void __launch_bounds__(BS)
+    gs_dataflow_kernel(int ntasks, const int4* __restrict__ tasks, const int* __restrict__ wave_ntasks, unsigned* counters,
+                       const int* __restrict__ perm, const int* __restrict__ pptr, const int* __restrict__ pcol,
+                       const double* __restrict__ pval, double* x, const double* __restrict__ b, double omega, int sor,
+                       int acquire_mode, int opaque_zero, unsigned long long* dbg) {
+  __shared__ int s_task[2];
+  const int tid = threadIdx.x, g = tid / T, lane = tid % T;
+  if (tid == 0) s_task[0] = (int)atomicAdd(&counters[0], 1u);
+  __syncthreads();
+  int cur = s_task[0], buf = 0;
+  while (cur < ntasks) {
+    if (tid == 0) s_task[buf ^ 1] = (int)atomicAdd(&counters[0], 1u);   // next ticket, off the critical path
+    const int4 tk = __ldg(tasks + cur);
+    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 0] = global_ns();
+    const bool active = g < tk.y;
+    int row = -1, ks = 0, ke = 0;
+    double bv = 0.0, xold = 0.0;
+    if (active) {
+      const int p = tk.x + g;
+      row = __ldg(perm + p);
+      ks = __ldg(pptr + p);
+      ke = __ldg(pptr + p + 1);
+      if (lane == 0) {
+        bv = __ldg(b + row);
+        if (sor) xold = __ldcg(x + row);   // only this row's own update ever writes x[row] during the sweep
+      }
+    }
+    int c[kGsPrefetch];
+    double v[kGsPrefetch];
+#pragma unroll
+    for (int j = 0; j < kGsPrefetch; ++j) {
+      const int k = ks + lane + j * T;
+      const bool in = k < ke;
+      c[j] = in ? __ldg(pcol + k) : -1;
+      v[j] = in ? __ldg(pval + k) : 0.0;
+    }
+    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 1] = global_ns();
+    if (tk.z > 0) {
+      if (tid == 0) {
+        const unsigned need = (unsigned)tk.w;   // tasks of wavefront tk.z - 1
+        const unsigned* flag = counters + (size_t)tk.z * kGsCounterStride;
+        if (tk.z >= kGsFarWaves) {   // far from the front: sleep instead of hammering L2
+          const unsigned* far = flag - (size_t)(kGsFarWaves - 1) * kGsCounterStride;   // wavefront tk.z - kGsFarWaves
+          while (ld_relaxed_u32(far) == 0u) __nanosleep(500);
+        }
+        while (ld_relaxed_u32(flag) < need) {}
+        if (dbg) dbg[(size_t)cur * 8 + 2] = global_ns();
+        // Acquire side.  The producers performed every x store at L2 (fence) before their count became
+        // visible there, and the gathers below are L1-bypassing loads issued after this bar.sync, so
+        // they read L2 no earlier than the observed count: no consumer fence is needed on this
+        // hardware.  acquire_mode 1/2 add the formal PTX acquire (re-read with ld.acquire / full fence).
+        if (acquire_mode == 1) (void)ld_acquire_u32(flag);
+        else if (acquire_mode == 2) __threadfence();
+      }
+      __syncthreads();
+    }
+    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 3] = global_ns();
+    // All gathers of the task leave in one burst (a single asm block: neither NVVM nor ptxas may sink
+    // a load down to its use), so the critical path pays ONE L2 round trip.  Padding slots read a
+    // global zero; the diagonal slot reads x[row] and is skipped below.
+    double xv[kGsPrefetch];
+    {
+      const double* a[kGsPrefetch];
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) a[j] = c[j] >= 0 ? x + c[j] : &g_gs_zero;
+      static_assert(kGsPrefetch == 8, "the burst below is written for 8 slots");
+      asm volatile(
+          "ld.global.cg.f64 %0, [%8];\n\t"
+          "ld.global.cg.f64 %1, [%9];\n\t"
+          "ld.global.cg.f64 %2, [%10];\n\t"
+          "ld.global.cg.f64 %3, [%11];\n\t"
+          "ld.global.cg.f64 %4, [%12];\n\t"
+          "ld.global.cg.f64 %5, [%13];\n\t"
+          "ld.global.cg.f64 %6, [%14];\n\t"
+          "ld.global.cg.f64 %7, [%15];"
+          : "=d"(xv[0]), "=d"(xv[1]), "=d"(xv[2]), "=d"(xv[3]), "=d"(xv[4]), "=d"(xv[5]), "=d"(xv[6]), "=d"(xv[7])
+          : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
+          : "memory");
+    }
+    {
+      // ptxas otherwise sinks each load down to its multiply, and in-order issue then serialises the
+      // eight L2 round trips (measured: 1.0 us of a 2.0 us hop).  Folding all eight results into one
+      // run-time zero that every product depends on pins the loads in front of the first wait.
+      int dep = __double2hiint(xv[0]);
+#pragma unroll
+      for (int j = 1; j < kGsPrefetch; ++j) dep &= __double2hiint(xv[j]);
+      dep &= opaque_zero;
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) xv[j] = __hiloint2double(__double2hiint(xv[j]) | dep, __double2loint(xv[j]));
+    }
+    double rsum = 0.0, d = 0.0;
+#pragma unroll
+    for (int j = 0; j < kGsPrefetch; ++j) {
+      if (c[j] == row && c[j] >= 0) d = v[j];
+      else rsum = __dadd_rn(rsum, __dmul_rn(v[j], xv[j]));   // padding adds an exact +0
+    }
+    for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {   // rows longer than T * kGsPrefetch
+      const int cc = __ldg(pcol + k);
+      const double vv = __ldg(pval + k);
+      if (cc == row) d = vv;
+      else rsum = __dadd_rn(rsum, __dmul_rn(vv, __ldcg(x + cc)));
+    }
+    if (T > 1) {
+      rsum = lanes_sum<T>(rsum);
+      d = lanes_sum<T>(d);
+    }
+    if (active && lane == 0 && d != 0.0) {
+      const double r = __dsub_rn(bv, rsum);
+      __stcg(x + row, sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d));
+    }
+    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 4] = global_ns();
+    __syncthreads();
+    if (tid == 0) {
+      if (dbg) dbg[(size_t)cur * 8 + 5] = global_ns();
+      __threadfence();   // release side: every row of this task (bar.sync above) is visible before the count
+      if (dbg) dbg[(size_t)cur * 8 + 6] = global_ns();
+      red_relaxed_inc(counters + (size_t)(1 + tk.z) * kGsCounterStride);
+      if (dbg) dbg[(size_t)cur * 8 + 7] = global_ns();
+    }
+    cur = s_task[buf ^ 1];
+    buf ^= 1;
+  }
+}
+}  // namespace b200amg

@@ -183,10 +183,19 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
 /* Engine options (before or after finalize).  USE_GRAPHS (default 1): replay each cycle type as a
  * captured CUDA graph.  TIME_RESIDUAL (default 0): b200amg_solve brackets the fine-level
  * convergence-residual kernel (multilevel.jl:188-189) of every iteration with a CUDA event pair on
- * the launching stream; read the per-iteration milliseconds back with b200amg_residual_timings. */
-enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1 };
+ * the launching stream; read the per-iteration milliseconds back with b200amg_residual_timings.
+ * STREAM_CHUNK (default 1): consecutive tiles each CTA of the TMA stream kernels takes per run
+ * (0 = one contiguous range per CTA).  GS_MODE (default 1): 1 = Gauss-Seidel/SOR as one persistent
+ * dataflow kernel per sweep, 0 = one launch per wavefront.  Cycle graphs already captured keep the
+ * values they were captured with. */
+enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1, B200AMG_OPT_STREAM_CHUNK = 2, B200AMG_OPT_GS_MODE = 3, B200AMG_OPT_GS_ACQUIRE = 4 };
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
 int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
+/* Diagnostics: run one dataflow Gauss-Seidel sweep (forward / backward) of `level` on the level's
+ * current vectors and return 8 %globaltimer stamps (ns) per task: claimed, prefetch issued, wait
+ * done, gathers may start, row written, CTA barrier passed, fence done, count published. */
+int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t backward, uint64_t* out, int64_t cap,
+                                  int64_t* ntasks);
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
 int32_t b200amg_get_stream(b200amg_handle_t h, void** stream);
 /* raw device pointers of the level-0 work vectors (x, b) for zero-copy callers (torch / CUDA.jl) */

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Per-kernel timing sweep on one GPU (CUDA events inside b200amg_time_kernel): fine and coarse
+level SpMV / residual / restriction / prolongation / pre-smoother, for several STREAM_CHUNK values.
+Usage: python tools/tune_kernels.py [--size 256] [--smoother gs|jacobi] [--chunks 1,2,4,0]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+
+import algebraicmultigrid_jl_b200 as amg  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--size", type=int, default=256)
+ap.add_argument("--smoother", default="jacobi")
+ap.add_argument("--chunks", default="1,2,4,16,0")
+ap.add_argument("--levels", type=int, default=3)
+ap.add_argument("--reps", type=int, default=20)
+args = ap.parse_args()
+n1 = args.size
+t0 = time.time()
+A = amg.poisson((n1, n1, n1))
+kw = {}
+if args.smoother == "jacobi":
+    sm = amg.Jacobi(2.0 / 3.0)
+    kw = dict(presmoother=sm, postsmoother=sm)
+ml = amg.ruge_stuben(A, **kw)
+dev = ml.device()
+print(f"setup+upload {time.time() - t0:.1f}s", flush=True)
+b = A.matvec(np.ones(A.n))
+x = np.zeros(A.n)
+dev.cycle(x, b, 0)     # fill the level vectors with real data
+names = {0: "spmv", 1: "residual", 2: "presmooth", 3: "restrict", 4: "prolong"}
+for chunk in [int(c) for c in args.chunks.split(",")]:
+    dev.set_option(2, chunk)
+    for lv in range(min(args.levels, dev.nlevels - 1)):
+        info = dev.level_info(lv)
+        n, nnz, nnzp = info["n"], info["nnz_a"], info["nnz_p"]
+        nc = dev.level_info(lv + 1)["n"]
+        alg = {0: 12 * nnz + 4 * (n + 1) + 16 * n, 1: 12 * nnz + 4 * (n + 1) + 24 * n,
+               2: (12 * nnz + 4 * (n + 1) + 24 * n) * (2 if args.smoother == "gs" else 1),
+               3: 12 * nnzp + 4 * (nc + 1) + 8 * n + 8 * nc, 4: 12 * nnzp + 4 * (n + 1) + 8 * nc + 16 * n}
+        out = {"chunk": chunk, "level": lv, "n": n, "nnz": nnz}
+        for what in range(5):
+            ms = dev.time_kernel(lv, what, reps=args.reps, flush_l2=(alg[what] < 512e6))
+            out[names[what]] = {"ms": round(ms, 4), "GBs": round(alg[what] / ms / 1e6, 1)}
+        print(json.dumps(out), flush=True)
+if args.smoother == "gs":
+    for mode in (1, 0):
+        dev.set_option(3, mode)
+        for lv in range(dev.nlevels - 1):
+            info = dev.level_info(lv)
+            n, nnz = info["n"], info["nnz_a"]
+            ms = dev.time_kernel(lv, 2, reps=5)
+            alg = 2 * (12 * nnz + 4 * (n + 1) + 24 * n)
+            print(json.dumps({"gs_mode": mode, "level": lv, "n": n, "nnz": nnz, "wavefronts": info["wavefronts"],
+                              "sgs_ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1),
+                              "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}), flush=True)
