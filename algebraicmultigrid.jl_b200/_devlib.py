@@ -29,7 +29,8 @@ SYMBOLS = [
     "b200amg_coarse_solve", "b200amg_norm", "b200amg_pcg", "b200amg_smoother_create", "b200amg_smoother_apply",
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
-    "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline",
+    "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
+    "b200amg_partition_info", "b200amg_partition_plan",
 ]
 
 
@@ -102,6 +103,9 @@ def lib():
             "b200amg_set_option": [vp, i32, dbl],
             "b200amg_residual_timings": [vp, vp, i32, C.POINTER(i32)],
             "b200amg_get_stream": [vp, C.POINTER(vp)],
+            "b200amg_nccl_unique_id": [vp, i64],
+            "b200amg_partition_info": [vp] + [C.POINTER(i64)] * 8,
+            "b200amg_partition_plan": [pcsc, pcsc, pcsc, i32, i32, vp, vp, vp, C.POINTER(i64), vp, vp, C.POINTER(i64), vp, vp, vp, i64],
             "b200amg_debug_gs_timeline": [vp, i32, i32, vp, i64, C.POINTER(i64)],
         }
         for name, args in sigs.items():
@@ -121,6 +125,33 @@ def _check(rc):
 
 def device_count() -> int:
     return int(lib().b200amg_device_count())
+
+
+def nccl_unique_id() -> bytes:
+    """The 128-byte ncclUniqueId rank 0 creates and broadcasts (``MultiLevel.partition``)."""
+    buf = C.create_string_buffer(128)
+    _check(lib().b200amg_nccl_unique_id(C.cast(buf, C.c_void_p), 128))
+    return buf.raw
+
+
+def partition_plan(level, rank, world):
+    """Host-only partition plan of one ``Level`` (``b200amg_partition_plan``) as a dict of numpy arrays."""
+    keep = []
+    a, p, r = csc_desc(level.A, keep), csc_desc(level.P, keep), csc_desc(level.R, keep)
+    n = level.A.n
+    cap = n + 8
+    out = {"row_split": np.zeros(world + 1, np.int64), "coarse_split": np.zeros(world + 1, np.int64),
+           "halo_cols": np.zeros(cap, np.int32), "recv_off": np.zeros(world + 1, np.int32),
+           "send_idx": np.zeros(cap, np.int32), "send_off": np.zeros(world + 1, np.int32),
+           "cx_lo": np.zeros(world, np.int64), "cx_hi": np.zeros(world, np.int64)}
+    nhalo, nsend = C.c_int64(0), C.c_int64(0)
+    _check(lib().b200amg_partition_plan(C.byref(a), C.byref(p), C.byref(r), rank, world, _ptr(out["row_split"]),
+                                        _ptr(out["coarse_split"]), _ptr(out["halo_cols"]), C.byref(nhalo), _ptr(out["recv_off"]),
+                                        _ptr(out["send_idx"]), C.byref(nsend), _ptr(out["send_off"]), _ptr(out["cx_lo"]),
+                                        _ptr(out["cx_hi"]), cap))
+    out["halo_cols"] = out["halo_cols"][: nhalo.value].copy()
+    out["send_idx"] = out["send_idx"][: nsend.value].copy()
+    return out
 
 
 def _ptr(a):
@@ -285,6 +316,12 @@ class DeviceHierarchy:
         ms = np.zeros(cap)
         _check(lib().b200amg_profile_cycle(self._h, cycle, _ptr(ms), cap))
         return ms.reshape(self.nlevels, 6)
+
+    def partition_info(self):
+        v = [C.c_int64() for _ in range(8)]
+        _check(lib().b200amg_partition_info(self._h, *[C.byref(t) for t in v]))
+        keys = ["row_lo", "row_hi", "nhalo", "nsend", "coarse_lo", "coarse_hi", "cx_lo", "cx_hi"]
+        return {k: t.value for k, t in zip(keys, v)}
 
     def set_option(self, option, value):
         _check(lib().b200amg_set_option(self._h, int(option), float(value)))

@@ -15,10 +15,13 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is dlopen'ed when a partition is requested
 
 #include "b200amg.h"
 #include "kernels.cuh"
 #include "stream.cuh"
+#include "partition.h"
 
 using namespace b200amg;
 
@@ -69,6 +72,57 @@ struct AmgError {
     return fail(B200AMG_ERR_BAD_ARG, "%s", e.what());   \
   }                                                     \
   return B200AMG_OK;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (a single-GPU process never needs libnccl).  RTLD_NOLOAD first: a host
+// that already initialised torch.distributed has its NCCL loaded under the same soname.
+// ------------------------------------------------------------------------------------------
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  if (api.ok) return api;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) throw AmgError{B200AMG_ERR_NCCL, std::string("cannot load libnccl.so.2: ") + dlerror()};
+#define B200AMG_NCCL_SYM(field, name)                                                         \
+  api.field = reinterpret_cast<decltype(api.field)>(dlsym(lib, name));                          \
+  if (!api.field) throw AmgError{B200AMG_ERR_NCCL, std::string("libnccl lacks ") + name};
+  B200AMG_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  B200AMG_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  B200AMG_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  B200AMG_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+  B200AMG_NCCL_SYM(GroupStart, "ncclGroupStart")
+  B200AMG_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  B200AMG_NCCL_SYM(Send, "ncclSend")
+  B200AMG_NCCL_SYM(Recv, "ncclRecv")
+  B200AMG_NCCL_SYM(AllReduce, "ncclAllReduce")
+  B200AMG_NCCL_SYM(Broadcast, "ncclBroadcast")
+#undef B200AMG_NCCL_SYM
+  api.ok = true;
+  return api;
+}
+#define NCCL_OK(expr)                                                                                      \
+  do {                                                                                                     \
+    ncclResult_t _r = (expr);                                                                              \
+    if (_r != ncclSuccess) {                                                                               \
+      char _b[512];                                                                                        \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, nccl_api().GetErrorString(_r), __FILE__, __LINE__); \
+      throw AmgError{B200AMG_ERR_NCCL, _b};                                                                \
+    }                                                                                                      \
+  } while (0)
 
 // ------------------------------------------------------------------------------------------
 // host-side sparse staging (int32, 0-based, "by rows" = compressed along the first index)
@@ -411,14 +465,45 @@ static bool cfg_needs_bwd(const SmootherCfg& c) {
 
 struct Level {
   int64_t n = 0, nc = 0;
+  int64_t nnz_a = 0, nnz_p = 0;   // kept for level_info (a partitioned / remote level has no full device copy)
+  bool remote = false;            // this rank holds no device data for the level (rank != 0 of a partition)
   SmootherMatrix M;
   DevCsr P, R;
   SmootherCfg pre, post;
   double *res = nullptr, *coarse_x = nullptr, *coarse_b = nullptr, *temp = nullptr;
 };
 
+// The fine level of a row-partitioned hierarchy as one rank sees it (partition.h has the plan).
+struct Part {
+  PartPlan plan;
+  int64_t n = 0, nc = 0;
+  DevCsr A, At, R, P;            // local blocks; At aliases A when A is bit-symmetric
+  int symmetry = B200AMG_SYMMETRY_HERMITIAN;
+  SmootherCfg pre, post;
+  double* diag = nullptr;        // diagonal of the owned rows
+  int* send_idx = nullptr;
+  double* sendbuf = nullptr;
+  double *x = nullptr, *b = nullptr, *res = nullptr, *temp = nullptr;   // [owned | halo]
+  double *cb = nullptr, *cx = nullptr;   // my coarse_b rows / my coarse_x window (alias the full vectors on rank 0)
+  bool own_cb = false, own_cx = false;
+  double* xfull = nullptr;       // staging for the final all-gather when the caller's x is host memory
+  const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
+  void release() {
+    A.release(); At.release(); R.release(); P.release();
+    cudaFree(diag); cudaFree(send_idx); cudaFree(sendbuf); cudaFree(x); cudaFree(b); cudaFree(res); cudaFree(temp);
+    if (own_cb) cudaFree(cb);
+    if (own_cx) cudaFree(cx);
+    cudaFree(xfull);
+  }
+};
+
 struct b200amg_hierarchy {
   int device = 0;
+  // row partition of the fine level (world == 1: none)
+  int rank = 0, world = 1;
+  ncclUniqueId nccl_id;
+  ncclComm_t comm = nullptr;
+  std::unique_ptr<Part> part;
   cudaStream_t stream = nullptr;
   std::vector<std::unique_ptr<Level>> levels;
   // coarsest
@@ -449,6 +534,7 @@ struct b200amg_hierarchy {
   bool finalized = false;
   bool capturing = false;
   int64_t launches = 0;       // kernels launched (graph replays add their node counts)
+  int64_t collectives = 0;    // NCCL groups / collectives enqueued (partitioned handles)
   int64_t capture_count = 0;  // kernels recorded into the graph being captured
   // L2 flush buffer for time_kernel
   void* flush = nullptr;
@@ -463,6 +549,7 @@ struct b200amg_hierarchy {
 };
 typedef b200amg_hierarchy H;
 
+static void cycle_body_part(H* h, int cycle);
 static inline void count_launch(H* h) {
   if (h->capturing) h->capture_count++; else h->launches++;
 }
@@ -761,6 +848,7 @@ static void ensure_cycle_graph(H* h, int cycle) {
 }
 
 static void run_cycle(H* h, int cycle) {
+  if (h->part) { cycle_body_part(h, cycle); return; }
   ensure_cycle_graph(h, cycle);
   if (h->cycle_graph[cycle]) {
     CUDA_OK(cudaGraphLaunch(h->cycle_graph[cycle], h->stream));
@@ -784,6 +872,159 @@ static void residual_norm(H* h) {
   norm2_async(h, h->n0, res, h->scalars);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Row-partitioned fine level (config C4): halo exchange over NCCL, coarse levels on rank 0
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) halo_pack_kernel(int n, const int* __restrict__ idx, const double* __restrict__ v,
+                                                             double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = v[idx[i]];
+}
+
+// v is laid out [owned | halo]: gather what the neighbours need, exchange, receive straight into the halo
+static void halo_exchange(H* h, double* v) {
+  Part& P = *h->part;
+  const PartPlan& pl = P.plan;
+  NcclApi& nc = nccl_api();
+  const int nsend = pl.send_off[pl.world];
+  if (nsend > 0) {
+    halo_pack_kernel<<<grid_for(nsend), kThreads, 0, h->stream>>>(nsend, P.send_idx, v, P.sendbuf);
+    count_launch(h);
+  }
+  NCCL_OK(nc.GroupStart());
+  for (int q = 0; q < pl.world; ++q) {
+    if (q == pl.rank) continue;
+    const int ns = pl.send_off[q + 1] - pl.send_off[q], nr = pl.recv_off[q + 1] - pl.recv_off[q];
+    if (ns > 0) NCCL_OK(nc.Send(P.sendbuf + pl.send_off[q], (size_t)ns, ncclDouble, q, h->comm, h->stream));
+    if (nr > 0) NCCL_OK(nc.Recv(v + pl.nloc + pl.recv_off[q], (size_t)nr, ncclDouble, q, h->comm, h->stream));
+  }
+  NCCL_OK(nc.GroupEnd());
+  h->collectives++;
+}
+
+static void smooth_part(H* h, const SmootherCfg& c) {
+  Part& P = *h->part;
+  if (c.kind == B200AMG_SMOOTHER_NONE || P.plan.nloc == 0) {
+    if (c.kind != B200AMG_SMOOTHER_NONE) for (int it = 0; it < c.iter; ++it) halo_exchange(h, P.x);   // keep the collectives matched
+    return;
+  }
+  double* cur = P.x;
+  double* other = P.temp;
+  for (int it = 0; it < c.iter; ++it) {
+    halo_exchange(h, cur);
+    if (P.symmetry == B200AMG_SYMMETRY_NONE) launch_jacobi_general(h, P.A, P.diag, cur, P.b, other, c.omega);
+    else launch_jacobi_fast(h, P.walked(), cur, P.b, other, c.omega);
+    std::swap(cur, other);
+  }
+  if (cur != P.x) CUDA_OK(cudaMemcpyAsync(P.x, cur, sizeof(double) * (size_t)P.plan.nloc, cudaMemcpyDeviceToDevice, h->stream));
+}
+
+static void solve_level(H* h, double* x, int cycle, const double* b, int lvl, bool x_is_zero);
+static void coarse_solve(H* h, double* x, const double* b);
+
+// __solve!(x, ml, cycle, b, 1) with level 1 split by rows (multilevel.jl:214-239)
+static void cycle_body_part(H* h, int cycle) {
+  Part& P = *h->part;
+  const PartPlan& pl = P.plan;
+  NcclApi& nc = nccl_api();
+  Level& L0 = *h->levels[0];
+  smooth_part(h, P.pre);                                                         // :216
+  halo_exchange(h, P.x);
+  residual(h, P.A, P.x, P.b, P.res);                                            // :219-220
+  halo_exchange(h, P.res);
+  spmv(h, P.R, P.res, P.cb);                                                     // :223 (my coarse rows)
+  NCCL_OK(nc.GroupStart());                                                      // coarse_b -> rank 0
+  if (pl.rank == 0) {
+    for (int q = 1; q < pl.world; ++q) {
+      const int64_t cnt = pl.coarse_split[q + 1] - pl.coarse_split[q];
+      if (cnt > 0) NCCL_OK(nc.Recv(L0.coarse_b + pl.coarse_split[q], (size_t)cnt, ncclDouble, q, h->comm, h->stream));
+    }
+  } else if (pl.ncloc > 0) {
+    NCCL_OK(nc.Send(P.cb, (size_t)pl.ncloc, ncclDouble, 0, h->comm, h->stream));
+  }
+  NCCL_OK(nc.GroupEnd());
+  h->collectives++;
+  if (pl.rank == 0) {
+    CUDA_OK(cudaMemsetAsync(L0.coarse_x, 0, sizeof(double) * (size_t)std::max<int64_t>(L0.nc, 1), h->stream));   // :226
+    if (h->levels.size() == 1) {
+      coarse_solve(h, L0.coarse_x, L0.coarse_b);                                  // :228
+    } else if (cycle == B200AMG_CYCLE_V) {
+      solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, true);
+    } else if (cycle == B200AMG_CYCLE_W) {
+      solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, true);
+      solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, false);
+    } else {
+      solve_level(h, L0.coarse_x, B200AMG_CYCLE_F, L0.coarse_b, 1, true);
+      solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, false);
+    }
+  }
+  NCCL_OK(nc.GroupStart());                                                      // coarse_x windows <- rank 0
+  if (pl.rank == 0) {
+    for (int q = 1; q < pl.world; ++q) {
+      const int64_t cnt = pl.cx_hi_all[q] - pl.cx_lo_all[q];
+      if (cnt > 0) NCCL_OK(nc.Send(L0.coarse_x + pl.cx_lo_all[q], (size_t)cnt, ncclDouble, q, h->comm, h->stream));
+    }
+  } else if (pl.cx_hi > pl.cx_lo) {
+    NCCL_OK(nc.Recv(P.cx, (size_t)(pl.cx_hi - pl.cx_lo), ncclDouble, 0, h->comm, h->stream));
+  }
+  NCCL_OK(nc.GroupEnd());
+  h->collectives++;
+  spmv_add(h, P.P, P.cx, P.x);                                                   // :233-234
+  smooth_part(h, P.post);                                                        // :236
+}
+
+// sum over ranks of a device scalar, in place; every rank gets the same bits
+static void allreduce_scalar(H* h, double* dev) {
+  NCCL_OK(nccl_api().AllReduce(dev, dev, 1, ncclDouble, ncclSum, h->comm, h->stream));
+  h->collectives++;
+}
+// scalars[slot] = sum over all ranks of v.v over the owned entries (NOT square-rooted)
+static void sumsq_part(H* h, const double* v, double* out_dev) {
+  dot_partial_kernel<<<kRedBlocks, kThreads, 0, h->stream>>>(h->part->plan.nloc, v, v, h->partial);
+  count_launch(h);
+  reduce_final_kernel<<<1, kThreads, 0, h->stream>>>(kRedBlocks, h->partial, out_dev, 0);
+  count_launch(h);
+  allreduce_scalar(h, out_dev);
+}
+static void residual_norm_part(H* h) {   // scalars[0] = ||b - A x||^2 over all ranks
+  Part& P = *h->part;
+  halo_exchange(h, P.x);
+  const bool timed = h->time_residual && h->res_events_used + 2 <= (int)h->res_events.size();
+  if (timed) CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used], h->stream));
+  residual(h, P.A, P.x, P.b, P.res);
+  if (timed) {
+    CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used + 1], h->stream));
+    h->res_events_used += 2;
+  }
+  sumsq_part(h, P.res, h->scalars);
+}
+// owned slice in, assembled vector out
+static void part_load(H* h, double* dst, const double* src_full, int memkind) {
+  const PartPlan& pl = h->part->plan;
+  if (pl.nloc == 0) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src_full + pl.row_split[pl.rank], sizeof(double) * (size_t)pl.nloc,
+                          memkind == B200AMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, h->stream));
+}
+static void part_store(H* h, double* dst_full, const double* src_local, int memkind) {
+  Part& P = *h->part;
+  const PartPlan& pl = P.plan;
+  NcclApi& nc = nccl_api();
+  double* full = dst_full;
+  if (memkind == B200AMG_MEM_HOST) {
+    if (!P.xfull) P.xfull = dev_alloc<double>(P.n);
+    full = P.xfull;
+  }
+  NCCL_OK(nc.GroupStart());
+  for (int q = 0; q < pl.world; ++q) {
+    const int64_t cnt = pl.row_split[q + 1] - pl.row_split[q];
+    if (cnt > 0) NCCL_OK(nc.Broadcast(q == pl.rank ? src_local : full + pl.row_split[q], full + pl.row_split[q], (size_t)cnt, ncclDouble, q, h->comm, h->stream));
+  }
+  NCCL_OK(nc.GroupEnd());
+  h->collectives++;
+  if (memkind == B200AMG_MEM_HOST) CUDA_OK(cudaMemcpyAsync(dst_full, full, sizeof(double) * (size_t)P.n, cudaMemcpyDeviceToHost, h->stream));
+}
+
 // ------------------------------------------------------------------------------------------
 // API helpers
 // ------------------------------------------------------------------------------------------
@@ -792,6 +1033,9 @@ static void check_ready(H* h) {
   REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
   REQUIRE(h->finalized, B200AMG_ERR_STATE, "hierarchy not finalized (call b200amg_finalize first)");
   set_device(h);
+}
+static void check_not_partitioned(H* h, const char* what) {
+  REQUIRE(!h->part, B200AMG_ERR_UNSUPPORTED, "%s is not available on a row-partitioned handle (use solve / cycle / precond)", what);
 }
 static void to_dev(H* h, double* dst, const double* src, int64_t n, int memkind) {
   if (n == 0) return;
@@ -842,6 +1086,47 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   API_END
 }
 
+// level 1 of a partitioned hierarchy: local blocks, halo plan, local vectors
+static void build_part(H* h, Level& L, const HostCsr& hAt, const HostCsr& hP, const HostCsr& hR, int symmetry) {
+  std::unique_ptr<Part> part(new Part());
+  Part& P = *part;
+  P.n = L.n; P.nc = L.nc; P.symmetry = symmetry; P.pre = L.pre; P.post = L.post;
+  auto ok = [](const SmootherCfg& c) { return c.kind == B200AMG_SMOOTHER_NONE || c.kind == B200AMG_SMOOTHER_JACOBI; };
+  REQUIRE(ok(L.pre) && ok(L.post), B200AMG_ERR_UNSUPPORTED,
+          "Gauss-Seidel / SOR do not shard (the sweep is sequential over the whole index range): use Jacobi on a partitioned fine level");
+  HostCsr hA = transpose(hAt);
+  const bool sym = bit_equal(hA, hAt);
+  P.plan = make_part_plan(h->rank, h->world, hA, sym ? nullptr : &hAt, hR, hP);
+  const PartPlan& pl = P.plan;
+  const int64_t lo = pl.row_split[pl.rank], hi = pl.row_split[pl.rank + 1];
+  P.A.upload(part_local_block(hA, lo, hi, lo, hi, pl.halo_cols));
+  if (sym) P.At.alias(P.A);
+  else P.At.upload(part_local_block(hAt, lo, hi, lo, hi, pl.halo_cols));
+  P.R.upload(part_local_block(hR, pl.coarse_split[pl.rank], pl.coarse_split[pl.rank + 1], lo, hi, pl.halo_cols));
+  P.P.upload(part_shifted_block(hP, lo, hi, pl.cx_lo, pl.cx_hi - pl.cx_lo));
+  {
+    const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt : hA;
+    std::vector<double> d((size_t)pl.nloc, 0.0);
+    for (int64_t i = lo; i < hi; ++i)
+      for (int k = w.ptr[i]; k < w.ptr[i + 1]; ++k)
+        if (w.idx[k] == i) d[i - lo] = w.val[k];
+    P.diag = dev_upload(d);
+  }
+  P.send_idx = dev_upload(pl.send_idx);
+  P.sendbuf = dev_alloc<double>((int64_t)pl.send_idx.size());
+  const int64_t nv = pl.nloc + pl.nhalo + 8;
+  P.x = dev_alloc<double>(nv); P.b = dev_alloc<double>(nv); P.res = dev_alloc<double>(nv); P.temp = dev_alloc<double>(nv);
+  for (double* v : {P.x, P.b, P.res, P.temp}) CUDA_OK(cudaMemset(v, 0, sizeof(double) * (size_t)nv));
+  if (pl.rank == 0) {   // my coarse rows / window are slices of the full vectors
+    P.cb = L.coarse_b + pl.coarse_split[0];
+    P.cx = L.coarse_x + pl.cx_lo;
+  } else {
+    P.cb = dev_alloc<double>(pl.ncloc + 8); P.own_cb = true;
+    P.cx = dev_alloc<double>(pl.cx_hi - pl.cx_lo + 8); P.own_cx = true;
+  }
+  h->part = std::move(part);
+}
+
 int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R,
                           const b200amg_smoother_t* pre, const b200amg_smoother_t* post, int32_t symmetry) {
   API_BEGIN
@@ -857,6 +1142,8 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
   if (!h->levels.empty())
     REQUIRE(h->levels.back()->nc == L->n, B200AMG_ERR_DIM_MISMATCH, "level has %lld rows but the previous level coarsens to %lld",
             (long long)L->n, (long long)h->levels.back()->nc);
+  const bool fine_of_partition = h->world > 1 && h->levels.empty();
+  const bool remote = h->world > 1 && !h->levels.empty() && h->rank != 0;   // coarse levels live on rank 0 only
   {
     HostCsr hP = stage_operator_by_rows(P);
     HostCsr hR = stage_operator_by_rows(R);
@@ -865,17 +1152,28 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
     REQUIRE(hR.nrows == hP.ncols, B200AMG_ERR_DIM_MISMATCH, "R has %lld rows but P has %lld columns", (long long)hR.nrows,
             (long long)hP.ncols);
     L->nc = hR.nrows;
-    L->P.upload(hP);
-    L->R.upload(hR);
-  }
-  {
+    L->nnz_p = hP.nnz();
     HostCsr hAt = stage_csc_as_rows_of_transpose(A);
-    L->M.build(hAt, symmetry, cfg_needs_fwd(L->pre) || cfg_needs_fwd(L->post), cfg_needs_bwd(L->pre) || cfg_needs_bwd(L->post), true);
+    L->nnz_a = hAt.nnz();
+    if (fine_of_partition) {
+      if (h->rank == 0) {
+        L->coarse_x = dev_alloc<double>(L->nc + 8);
+        L->coarse_b = dev_alloc<double>(L->nc + 8);
+      }
+      L->remote = true;   // no full device copy of this level on any rank
+      build_part(h, *L, hAt, hP, hR, symmetry);
+    } else if (remote) {
+      L->remote = true;
+    } else {
+      L->P.upload(hP);
+      L->R.upload(hR);
+      L->M.build(hAt, symmetry, cfg_needs_fwd(L->pre) || cfg_needs_fwd(L->post), cfg_needs_bwd(L->pre) || cfg_needs_bwd(L->post), true);
+      L->res = dev_alloc<double>(L->n + 8);
+      L->temp = dev_alloc<double>(L->n + 8);
+      L->coarse_x = dev_alloc<double>(L->nc + 8);
+      L->coarse_b = dev_alloc<double>(L->nc + 8);
+    }
   }
-  L->res = dev_alloc<double>(L->n);
-  L->temp = dev_alloc<double>(L->n);
-  L->coarse_x = dev_alloc<double>(L->nc);
-  L->coarse_b = dev_alloc<double>(L->nc);
   h->levels.push_back(std::move(L));
   API_END
 }
@@ -892,20 +1190,86 @@ int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int
     REQUIRE(h->levels.back()->nc == n, B200AMG_ERR_DIM_MISMATCH, "coarsest matrix has %lld rows, last level coarsens to %lld",
             (long long)n, (long long)h->levels.back()->nc);
   set_device(h);
-  HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
-  h->finalA.upload(transpose(hAt));
+  REQUIRE(h->world == 1 || !h->levels.empty(), B200AMG_ERR_UNSUPPORTED, "a partitioned hierarchy needs at least one level");
   h->nfinal = n;
-  std::vector<double> m(inv, inv + n * n);
-  h->coarse_inv = dev_upload(m);
-  h->res_final = dev_alloc<double>(n);
+  if (h->world == 1 || h->rank == 0) {
+    HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
+    h->finalA.upload(transpose(hAt));
+    std::vector<double> m(inv, inv + n * n);
+    h->coarse_inv = dev_upload(m);
+    h->res_final = dev_alloc<double>(n);
+  }
   h->have_coarse = true;
   API_END
 }
 
 int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_size, const void* id, int64_t id_bytes) {
-  (void)h; (void)rank; (void)id; (void)id_bytes;
-  if (world_size == 1) return B200AMG_OK;
-  return fail(B200AMG_ERR_UNSUPPORTED, "row-partitioned fine level not available in this build");
+  API_BEGIN
+  REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  REQUIRE(!h->finalized && h->levels.empty(), B200AMG_ERR_STATE, "set_partition must precede add_level");
+  REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, B200AMG_ERR_BAD_ARG, "bad rank %d / world size %d", rank, world_size);
+  if (world_size > 1) {
+    REQUIRE(id && id_bytes == (int64_t)sizeof(ncclUniqueId), B200AMG_ERR_BAD_ARG, "nccl unique id must be %d bytes", (int)sizeof(ncclUniqueId));
+    nccl_api();   // fail early if NCCL cannot be loaded
+    std::memcpy(&h->nccl_id, id, sizeof(ncclUniqueId));
+  }
+  h->rank = rank;
+  h->world = world_size;
+  API_END
+}
+
+int32_t b200amg_nccl_unique_id(void* out, int64_t cap) {
+  API_BEGIN
+  REQUIRE(out && cap >= (int64_t)sizeof(ncclUniqueId), B200AMG_ERR_BAD_ARG, "buffer must hold %d bytes", (int)sizeof(ncclUniqueId));
+  ncclUniqueId id;
+  NCCL_OK(nccl_api().GetUniqueId(&id));
+  std::memcpy(out, &id, sizeof id);
+  API_END
+}
+
+// Host-only: the plan one rank of a `world`-way partition would use (no device needed; what the CPU
+// world_size-2 tests exercise).  Array capacities: row_split/coarse_split/recv_off/send_off world+1,
+// cx_lo/cx_hi world, halo_cols/send_idx `cap` entries.
+int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, int32_t rank, int32_t world,
+                               int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                               int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap) {
+  API_BEGIN
+  REQUIRE(A && P && R && row_split && coarse_split && halo_cols && nhalo && recv_off && send_idx && nsend && send_off && cx_lo && cx_hi,
+          B200AMG_ERR_BAD_ARG, "null argument");
+  REQUIRE(world >= 1 && rank >= 0 && rank < world, B200AMG_ERR_BAD_ARG, "bad rank / world");
+  HostCsr hAt = stage_csc_as_rows_of_transpose(A);
+  HostCsr hA = transpose(hAt);
+  const bool sym = bit_equal(hA, hAt);
+  HostCsr hP = stage_operator_by_rows(P), hR = stage_operator_by_rows(R);
+  PartPlan pl = make_part_plan(rank, world, hA, sym ? nullptr : &hAt, hR, hP);
+  REQUIRE((int64_t)pl.halo_cols.size() <= cap && (int64_t)pl.send_idx.size() <= cap, B200AMG_ERR_BAD_ARG, "capacity too small");
+  std::copy(pl.row_split.begin(), pl.row_split.end(), row_split);
+  std::copy(pl.coarse_split.begin(), pl.coarse_split.end(), coarse_split);
+  std::copy(pl.halo_cols.begin(), pl.halo_cols.end(), halo_cols);
+  std::copy(pl.recv_off.begin(), pl.recv_off.end(), recv_off);
+  std::copy(pl.send_idx.begin(), pl.send_idx.end(), send_idx);
+  std::copy(pl.send_off.begin(), pl.send_off.end(), send_off);
+  std::copy(pl.cx_lo_all.begin(), pl.cx_lo_all.end(), cx_lo);
+  std::copy(pl.cx_hi_all.begin(), pl.cx_hi_all.end(), cx_hi);
+  *nhalo = pl.nhalo;
+  *nsend = (int64_t)pl.send_idx.size();
+  API_END
+}
+
+int32_t b200amg_partition_info(b200amg_handle_t h, int64_t* row_lo, int64_t* row_hi, int64_t* nhalo, int64_t* nsend,
+                               int64_t* coarse_lo, int64_t* coarse_hi, int64_t* cx_lo, int64_t* cx_hi) {
+  API_BEGIN
+  REQUIRE(h && h->part, B200AMG_ERR_STATE, "handle is not partitioned");
+  const PartPlan& pl = h->part->plan;
+  if (row_lo) *row_lo = pl.row_split[pl.rank];
+  if (row_hi) *row_hi = pl.row_split[pl.rank + 1];
+  if (nhalo) *nhalo = pl.nhalo;
+  if (nsend) *nsend = (int64_t)pl.send_idx.size();
+  if (coarse_lo) *coarse_lo = pl.coarse_split[pl.rank];
+  if (coarse_hi) *coarse_hi = pl.coarse_split[pl.rank + 1];
+  if (cx_lo) *cx_lo = pl.cx_lo;
+  if (cx_hi) *cx_hi = pl.cx_hi;
+  API_END
 }
 
 int32_t b200amg_finalize(b200amg_handle_t h) {
@@ -915,10 +1279,16 @@ int32_t b200amg_finalize(b200amg_handle_t h) {
   REQUIRE(h->have_coarse, B200AMG_ERR_STATE, "b200amg_set_coarse has not been called");
   set_device(h);
   h->n0 = h->levels.empty() ? h->nfinal : h->levels[0]->n;
-  h->x0 = dev_alloc<double>(h->n0);
-  h->b0 = dev_alloc<double>(h->n0);
-  CUDA_OK(cudaMemset(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1)));
-  CUDA_OK(cudaMemset(h->b0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1)));
+  if (h->world > 1) {
+    REQUIRE(h->part, B200AMG_ERR_STATE, "partitioned hierarchy without a fine level");
+    NCCL_OK(nccl_api().CommInitRank(&h->comm, h->world, h->nccl_id, h->rank));
+    h->use_graphs = false;
+  } else {
+    h->x0 = dev_alloc<double>(h->n0 + 8);
+    h->b0 = dev_alloc<double>(h->n0 + 8);
+    CUDA_OK(cudaMemset(h->x0, 0, sizeof(double) * (size_t)(h->n0 + 8)));
+    CUDA_OK(cudaMemset(h->b0, 0, sizeof(double) * (size_t)(h->n0 + 8)));
+  }
   h->finalized = true;
   API_END
 }
@@ -931,6 +1301,8 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
     L->M.release(); L->P.release(); L->R.release();
     cudaFree(L->res); cudaFree(L->temp); cudaFree(L->coarse_x); cudaFree(L->coarse_b);
   }
+  if (h->part) h->part->release();
+  if (h->comm) nccl_api().CommDestroy(h->comm);
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
   cudaFree(h->partial); cudaFree(h->scalars); cudaFreeHost(h->h_scalars);
@@ -953,8 +1325,13 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
   const int64_t n = h->n0;
-  to_dev(h, h->b0, b, n, memkind);
-  to_dev(h, h->x0, x, n, memkind);
+  if (h->part) {
+    part_load(h, h->part->b, b, memkind);
+    part_load(h, h->part->x, x, memkind);
+  } else {
+    to_dev(h, h->b0, b, n, memkind);
+    to_dev(h, h->x0, x, n, memkind);
+  }
   int nr = 0;
   h->res_events_used = 0;
   if (h->time_residual) {
@@ -965,21 +1342,34 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
       h->res_events.push_back(e);
     }
   }
-  norm2_async(h, n, h->b0, h->scalars);
-  double normb = read_scalar(h, h->scalars), normres = normb;                        // :170
+  double normb;
+  if (h->part) {
+    sumsq_part(h, h->part->b, h->scalars);
+    normb = std::sqrt(read_scalar(h, h->scalars));
+  } else {
+    norm2_async(h, n, h->b0, h->scalars);
+    normb = read_scalar(h, h->scalars);
+  }
+  double normres = normb;                                                              // :170
   if (normb != 0) abstol = std::max(reltol * normb, abstol);                           // :171-173
   if (residuals && nr < cap) residuals[nr++] = normb;                                  // :174
   int itr = 1;
   while (itr <= maxiter && (!calculate_residual || normres > abstol)) {                // :178
     run_cycle(h, cycle);                                                               // :179-183
     if (calculate_residual) {
-      residual_norm(h);                                                                // :188-190
-      normres = read_scalar(h, h->scalars);
+      if (h->part) {
+        residual_norm_part(h);
+        normres = std::sqrt(read_scalar(h, h->scalars));
+      } else {
+        residual_norm(h);                                                              // :188-190
+        normres = read_scalar(h, h->scalars);
+      }
       if (residuals && nr < cap) residuals[nr++] = normres;                            // :191
     }
     itr += 1;
   }
-  from_dev(h, x, h->x0, n, memkind);
+  if (h->part) part_store(h, x, h->part->x, memkind);
+  else from_dev(h, x, h->x0, n, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   if (nres) *nres = nr;
   if (iters) *iters = itr - 1;
@@ -991,10 +1381,17 @@ int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cy
   check_ready(h);
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
-  to_dev(h, h->b0, b, h->n0, memkind);
-  to_dev(h, h->x0, x, h->n0, memkind);
-  run_cycle(h, cycle);
-  from_dev(h, x, h->x0, h->n0, memkind);
+  if (h->part) {
+    part_load(h, h->part->b, b, memkind);
+    part_load(h, h->part->x, x, memkind);
+    run_cycle(h, cycle);
+    part_store(h, x, h->part->x, memkind);
+  } else {
+    to_dev(h, h->b0, b, h->n0, memkind);
+    to_dev(h, h->x0, x, h->n0, memkind);
+    run_cycle(h, cycle);
+    from_dev(h, x, h->x0, h->n0, memkind);
+  }
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1005,6 +1402,16 @@ int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t 
   check_ready(h);
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  if (h->part) {
+    Part& P = *h->part;
+    part_load(h, P.b, b, memkind);
+    if (init_zero) CUDA_OK(cudaMemsetAsync(P.x, 0, sizeof(double) * (size_t)std::max<int64_t>(P.plan.nloc, 1), h->stream));
+    else CUDA_OK(cudaMemcpyAsync(P.x, P.b, sizeof(double) * (size_t)P.plan.nloc, cudaMemcpyDeviceToDevice, h->stream));
+    run_cycle(h, cycle);
+    part_store(h, x, P.x, memkind);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return B200AMG_OK;
+  }
   to_dev(h, h->b0, b, h->n0, memkind);
   if (init_zero) CUDA_OK(cudaMemsetAsync(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1), h->stream));
   else CUDA_OK(cudaMemcpyAsync(h->x0, h->b0, sizeof(double) * h->n0, cudaMemcpyDeviceToDevice, h->stream));
@@ -1017,6 +1424,7 @@ int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t 
 int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double* x, const double* b, int32_t memkind) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "smooth");
   REQUIRE(level >= 0 && level < (int)h->levels.size(), B200AMG_ERR_BAD_ARG, "level %d out of range", level);
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   Level& L = *h->levels[level];
@@ -1032,6 +1440,7 @@ int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double*
 int32_t b200amg_apply(b200amg_handle_t h, int32_t level, int32_t op, double* y, const double* x, int32_t memkind) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "apply");
   REQUIRE(y && x, B200AMG_ERR_BAD_ARG, "null vector");
   const int nl = (int)h->levels.size();
   const DevCsr* A = nullptr;
@@ -1053,6 +1462,7 @@ int32_t b200amg_apply(b200amg_handle_t h, int32_t level, int32_t op, double* y, 
 int32_t b200amg_residual(b200amg_handle_t h, int32_t level, double* r, const double* b, const double* x, int32_t memkind) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "residual");
   REQUIRE(r && b && x, B200AMG_ERR_BAD_ARG, "null vector");
   const int nl = (int)h->levels.size();
   REQUIRE(level >= 0 && level <= nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
@@ -1069,6 +1479,7 @@ int32_t b200amg_residual(b200amg_handle_t h, int32_t level, double* r, const dou
 int32_t b200amg_coarse_solve(b200amg_handle_t h, double* x, const double* b, int32_t memkind) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "coarse_solve");
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   Scratch sx(h->nfinal), sb(h->nfinal);
   to_dev(h, sb.p, b, h->nfinal, memkind);
@@ -1101,6 +1512,7 @@ int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycl
                     double reltol, double* residuals, int32_t cap, int32_t* nres, int32_t* iters, int32_t memkind) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "pcg");
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
   const int64_t n = h->n0;
@@ -1218,8 +1630,8 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
   } else {
     Level& L = *h->levels[level];
     if (n) *n = L.n;
-    if (nnz_a) *nnz_a = L.M.At.nnz;
-    if (nnz_p) *nnz_p = L.P.nnz;
+    if (nnz_a) *nnz_a = L.nnz_a;
+    if (nnz_p) *nnz_p = L.nnz_p;
     if (wavefronts) *wavefronts = L.M.fwd.built ? L.M.fwd.nlev : (L.M.bwd.built ? L.M.bwd.nlev : 0);
   }
   API_END
@@ -1233,7 +1645,8 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
   check_ready(h);
   REQUIRE(ms && reps > 0, B200AMG_ERR_BAD_ARG, "bad argument");
   const int nl = (int)h->levels.size();
-  REQUIRE(what == 5 || what == 6 || (level >= 0 && level < nl), B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  REQUIRE(what == 5 || what == 6 || what == 7 || (level >= 0 && level < nl), B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  REQUIRE(what != 7 || h->part, B200AMG_ERR_BAD_ARG, "selector 7 (halo exchange) needs a partitioned handle");
   if (flush_l2 && !h->flush) {
     h->flush_bytes = (size_t)512 << 20;
     CUDA_OK(cudaMalloc(&h->flush, h->flush_bytes));
@@ -1248,6 +1661,21 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
     CUDA_OK(cudaEventRecord(e0, h->stream));
     if (what == 5) {
       run_cycle(h, cycle);
+    } else if (h->part) {
+      // per-rank view of the partitioned fine level: 0 local SpMV, 1 local residual, 2 pre-smoother
+      // (halo exchanges included), 6 local sum of squares + all-reduce, 7 one halo exchange
+      Part& P = *h->part;
+      REQUIRE(level == 0 || what == 6 || what == 7, B200AMG_ERR_UNSUPPORTED, "only the fine level of a partitioned handle can be timed");
+      switch (what) {
+        case 0: spmv(h, P.A, P.x, P.res); break;
+        case 1: residual(h, P.A, P.x, P.b, P.res); break;
+        case 2: smooth_part(h, P.pre); break;
+        case 3: spmv(h, P.R, P.res, P.cb); break;
+        case 4: spmv_add(h, P.P, P.cx, P.x); break;
+        case 6: sumsq_part(h, P.b, h->scalars + 4); break;
+        case 7: halo_exchange(h, P.x); break;
+        default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown kernel selector %d", what);
+      }
     } else if (what == 6) {
       norm2_async(h, h->n0, h->b0, h->scalars + 4);
     } else {
@@ -1279,6 +1707,7 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
 int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int32_t cap) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "profile_cycle");
   REQUIRE(ms && cap >= 6 * ((int)h->levels.size() + 1), B200AMG_ERR_BAD_ARG, "ms buffer too small");
   std::vector<double> acc((size_t)cap, 0.0);
   h->profiling = true;
@@ -1329,6 +1758,7 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
                                   int64_t* ntasks) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "gs timeline");
   REQUIRE(level >= 0 && level < (int)h->levels.size() && out && ntasks, B200AMG_ERR_BAD_ARG, "bad argument");
   Level& L = *h->levels[level];
   const DevSchedule& sc = backward ? L.M.bwd : L.M.fwd;
@@ -1360,6 +1790,7 @@ int32_t b200amg_get_stream(b200amg_handle_t h, void** stream) {
 int32_t b200amg_device_vectors(b200amg_handle_t h, double** x, double** b) {
   API_BEGIN
   check_ready(h);
+  check_not_partitioned(h, "device_vectors");
   if (x) *x = h->x0;
   if (b) *b = h->b0;
   API_END

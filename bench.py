@@ -263,19 +263,23 @@ def run_ours(args):
     achieved = alg / (res_ms_avg * 1e-3) / 1e9
     spmv_ms = dev.time_kernel(0, 0, reps=20)
     jac_or_gs_ms = dev.time_kernel(0, 2, reps=5)
+    halo_ms = dev.time_kernel(0, 7, reps=20) if world > 1 else None
     roofline = {"kernel": "csr residual r=b-A*x, fine level (convergence check of every `_solve!` iteration)",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
                 "avg_launch_ms": res_ms_avg, "launches_timed": int(len(res_ms)), "share_of_step": res_ms_avg / (ms / K),
                 "traffic": None}
-    prof = dev.profile_cycle(0)
     phases = ["presmoother", "residual", "restriction", "coarse_solve", "prolongation", "postsmoother"]
+    prof = dev.profile_cycle(0) if world == 1 else np.zeros((dev.nlevels, 6))
     infos = [dev.level_info(i) for i in range(dev.nlevels)]
+    pinfo = dev.partition_info() if world > 1 else None
+    nl, nnzl = (pinfo["row_hi"] - pinfo["row_lo"], nnz // world) if world > 1 else (n, nnz)
     extra = {
-        "fine_spmv_ms": spmv_ms, "fine_spmv_gbs": bytes_spmv(n, nnz) / (spmv_ms * 1e-3) / 1e9,
-        "fine_spmv_frac_of_measured_peak": bytes_spmv(n, nnz) / (spmv_ms * 1e-3) / 1e9 / peak,
-        "fine_presmoother_ms": jac_or_gs_ms,
-        "fine_presmoother_gbs": (2 if args.smoother == "gs" else 1) * bytes_residual(n, nnz) / (jac_or_gs_ms * 1e-3) / 1e9,
+        "fine_spmv_ms": spmv_ms, "fine_spmv_gbs": bytes_spmv(nl, nnzl) / (spmv_ms * 1e-3) / 1e9,
+        "fine_spmv_frac_of_measured_peak": bytes_spmv(nl, nnzl) / (spmv_ms * 1e-3) / 1e9 / peak,
+        "fine_spmv_note": "rank 0's row block, local kernel only" if world > 1 else "whole fine level",
+        "fine_presmoother_ms": jac_or_gs_ms, "halo_exchange_ms": halo_ms, "partition_rank0": pinfo,
+        "fine_presmoother_gbs": (2 if args.smoother == "gs" else 1) * bytes_residual(nl, nnzl) / (jac_or_gs_ms * 1e-3) / 1e9,
         "phase_ms_per_level": {ph: [round(float(v), 4) for v in prof[:, i]] for i, ph in enumerate(phases)},
         "levels": infos, "setup_s": t_setup, "upload_s": t_upload, "max_abs_err_vs_ones": err,
         "residual_history_first_last": [float(hist[0]), float(hist[-1])],

@@ -108,10 +108,29 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
  * QR/LU solvers (:66-81).  final_A is used when the hierarchy has no levels (multilevel.jl:167). */
 int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n,
                            const double* coarse_inverse_colmajor);
-/* Optional, before finalize: make this handle one rank of a row-partitioned fine level.
- * nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 and broadcast by the host. */
+/* Optional, BEFORE the first add_level: make this handle one rank (one process, one GPU) of a
+ * hierarchy whose FINE level is split by contiguous row blocks over world_size ranks; coarser
+ * levels live on rank 0.  Every rank then passes the SAME full hierarchy to add_level / set_coarse
+ * (each keeps only its part) and the same full-length x, b to solve / cycle / precond; x comes
+ * back assembled on every rank.  Fine-level smoothers must be Jacobi (Gauss-Seidel does not shard).
+ * nccl_unique_id: the 128-byte ncclUniqueId created on rank 0 (b200amg_nccl_unique_id) and
+ * broadcast by the host (torch.distributed / MPI / a file). */
 int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_size,
                               const void* nccl_unique_id, int64_t id_bytes);
+/* rank 0 creates the id (ncclGetUniqueId) that every rank passes to b200amg_set_partition; cap >= 128. */
+int32_t b200amg_nccl_unique_id(void* out, int64_t cap);
+/* what this rank holds of the partitioned fine level: owned rows [row_lo,row_hi), halo entries received /
+ * entries sent per exchange, restricted coarse rows [coarse_lo,coarse_hi), coarse_x window [cx_lo,cx_hi). */
+int32_t b200amg_partition_info(b200amg_handle_t h, int64_t* row_lo, int64_t* row_hi, int64_t* nhalo, int64_t* nsend,
+                               int64_t* coarse_lo, int64_t* coarse_hi, int64_t* cx_lo, int64_t* cx_hi);
+/* Host-only (no device needed): the partition plan rank `rank` of `world` derives for a fine level —
+ * row blocks, restricted coarse rows, the sorted halo column list with its per-owner segments
+ * (recv_off), the owned entries to send per destination (send_idx / send_off) and every rank's
+ * coarse_x window.  Capacities: *_split, recv_off, send_off: world+1; cx_lo, cx_hi: world;
+ * halo_cols, send_idx: cap. */
+int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, int32_t rank, int32_t world,
+                               int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                               int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap);
 /* builds device layouts (row-major operators, transposes, wavefront schedules), workspaces and
  * the captured cycle graphs. */
 int32_t b200amg_finalize(b200amg_handle_t h);
@@ -172,7 +191,8 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
 int64_t b200amg_launch_count(b200amg_handle_t h);
 /* Time `reps` back-to-back launches of one hot-path kernel on the handle's stream with CUDA
  * events; returns the average milliseconds per launch in *ms.  what: 0 spmv y=A x, 1 residual,
- * 2 pre-smoother, 3 restriction, 4 prolongation+correction, 5 one full cycle, 6 norm. */
+ * 2 pre-smoother, 3 restriction, 4 prolongation+correction, 5 one full cycle, 6 norm,
+ * 7 one halo exchange of the fine-level x (partitioned handles only). */
 int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int32_t cycle, int32_t reps,
                             int32_t flush_l2, double* ms);
 /* The six phases the reference times with @timeit_debug (src/multilevel.jl:216-236):
