@@ -210,40 +210,82 @@ static HostCsr stage_operator_by_rows(const b200amg_csc_t* M) {
   return transpose(t);                            // operator == stored
 }
 
-// Wavefront (level) schedule for an in-order sweep over rows 0..n-1 (forward) or n-1..0 (backward)
-// of `a`, honouring both true dependencies (a_ij, j earlier) and anti-dependencies (a_ji): the
-// dependency graph is the symmetrised pattern, which is why `at` (the transpose pattern) is needed.
-struct HostSchedule {
-  std::vector<int> rows;    // rows grouped by wavefront, ascending inside a wavefront
-  std::vector<int> lvlptr;  // nlev + 1
-};
-static HostSchedule build_schedule(const HostCsr& a, const HostCsr& at, bool forward) {
+// Wavefront (level) number of every row for an in-order FORWARD sweep over rows 0..n-1 of `a`, honouring
+// both true dependencies (a_ij, j earlier) and anti-dependencies (a_ji): the dependency graph is the
+// symmetrised pattern, which is why `at` (the transpose pattern) is needed.  The backward sweep walks
+// the same wavefronts in reverse order (level strictly increases along every edge, so the reversed
+// numbering is a valid schedule for the descending-index sweep).
+static std::vector<int> wavefront_levels(const HostCsr& a, const HostCsr& at, int* nlev_out) {
   const int64_t n = a.nrows;
   std::vector<int> level(n, 0);
   int nlev = 0;
-  for (int64_t s = 0; s < n; ++s) {
-    const int64_t i = forward ? s : n - 1 - s;
+  for (int64_t i = 0; i < n; ++i) {
     int lv = 0;
     for (int k = a.ptr[i]; k < a.ptr[i + 1]; ++k) {
       const int j = a.idx[k];
-      if (forward ? j < i : j > i) lv = std::max(lv, level[j] + 1);
+      if (j < i) lv = std::max(lv, level[j] + 1);
     }
     if (&at != &a)
       for (int k = at.ptr[i]; k < at.ptr[i + 1]; ++k) {
         const int j = at.idx[k];
-        if (forward ? j < i : j > i) lv = std::max(lv, level[j] + 1);
+        if (j < i) lv = std::max(lv, level[j] + 1);
       }
     level[i] = lv;
     nlev = std::max(nlev, lv + 1);
   }
-  HostSchedule sc;
-  sc.lvlptr.assign(nlev + 1, 0);
-  for (int64_t i = 0; i < n; ++i) sc.lvlptr[level[i] + 1]++;
-  for (int l = 0; l < nlev; ++l) sc.lvlptr[l + 1] += sc.lvlptr[l];
-  sc.rows.resize(n);
-  std::vector<int> next(sc.lvlptr.begin(), sc.lvlptr.end() - 1);
-  for (int64_t i = 0; i < n; ++i) sc.rows[next[level[i]]++] = (int)i;
-  return sc;
+  *nlev_out = nlev;
+  return level;
+}
+
+// A renumbering of one level: new index p holds old row old_of_new[p]; empty vectors = identity.
+struct HostPerm {
+  std::vector<int> new_of_old, old_of_new;
+  bool identity() const { return new_of_old.empty(); }
+};
+// rows AND columns renumbered; the order of the entries inside a row is kept (reference accumulation order)
+static HostCsr permute_sym(const HostCsr& m, const HostPerm& p) {
+  HostCsr out;
+  out.nrows = m.nrows; out.ncols = m.ncols;
+  out.ptr.resize(m.nrows + 1);
+  out.idx.resize(m.idx.size());
+  out.val.resize(m.val.size());
+  out.ptr[0] = 0;
+  for (int64_t q = 0; q < m.nrows; ++q) {
+    const int r = p.old_of_new[q];
+    out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
+  }
+  for (int64_t q = 0; q < m.nrows; ++q) {
+    const int r = p.old_of_new[q];
+    int o = out.ptr[q];
+    for (int k = m.ptr[r]; k < m.ptr[r + 1]; ++k, ++o) {
+      out.idx[o] = p.new_of_old[m.idx[k]];
+      out.val[o] = m.val[k];
+    }
+  }
+  return out;
+}
+static HostCsr permute_rows(const HostCsr& m, const HostPerm& p) {
+  if (p.identity()) return m;
+  HostCsr out;
+  out.nrows = m.nrows; out.ncols = m.ncols;
+  out.ptr.resize(m.nrows + 1);
+  out.idx.resize(m.idx.size());
+  out.val.resize(m.val.size());
+  out.ptr[0] = 0;
+  for (int64_t q = 0; q < m.nrows; ++q) {
+    const int r = p.old_of_new[q];
+    out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
+  }
+  for (int64_t q = 0; q < m.nrows; ++q) {
+    const int r = p.old_of_new[q];
+    std::copy(m.idx.begin() + m.ptr[r], m.idx.begin() + m.ptr[r + 1], out.idx.begin() + out.ptr[q]);
+    std::copy(m.val.begin() + m.ptr[r], m.val.begin() + m.ptr[r + 1], out.val.begin() + out.ptr[q]);
+  }
+  return out;
+}
+static void map_cols(HostCsr& m, const HostPerm& p) {
+  if (p.identity()) return;
+  for (int& c : m.idx) c = p.new_of_old[c];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -321,31 +363,47 @@ struct DevCsr {
 };
 
 struct SweepItem {
-  int lv_begin, lv_end;  // wavefront range
+  int lv_begin, lv_end;  // wavefront range (in sweep order)
   bool single_cta;
 };
+// One sweep direction over a level that has been renumbered into wavefront order: wavefront w of the
+// forward sweep is the contiguous row range [fwd_lvlptr[w], fwd_lvlptr[w+1]); the backward sweep takes the
+// same ranges last to first.
 struct DevSchedule {
   int nlev = 0;
   int64_t n = 0;
-  int* rows = nullptr;     // rows in schedule order (the permutation of the dataflow sweep)
+  int backward = 0;
+  int* rows = nullptr;     // rows in sweep order (identity or reversed blocks): per-wavefront fallback kernels only
   int* lvlptr = nullptr;
   std::vector<int> h_lvlptr;
   std::vector<SweepItem> items;
   bool built = false;
-  // dataflow sweep (stream.cuh: gs_dataflow_kernel): the walked matrix once more, rows in schedule order
+  // dataflow sweep (stream.cuh: gs_dataflow_kernel)
   int df_lanes = 1, df_threads = 128, ntasks = 0;
   int4* tasks = nullptr;
-  int* wave_ntasks = nullptr;
-  unsigned* counters = nullptr;   // [0] ticket, [1 + w] finished tasks of wavefront w
-  int *pptr = nullptr, *pcol = nullptr;
-  double* pval = nullptr;
-  void upload(const HostSchedule& h, const HostCsr& w, int lanes) {
-    nlev = (int)h.lvlptr.size() - 1;
-    n = (int64_t)h.rows.size();
-    rows = dev_upload(h.rows);
-    lvlptr = dev_upload(h.lvlptr);
-    h_lvlptr = h.lvlptr;
-    // group runs of narrow wavefronts into single-CTA items
+  unsigned* counters = nullptr;   // [0] ticket, [(1 + w) * kGsCounterStride] finished tasks of wavefront w
+  void upload(const std::vector<int>& fwd_lvlptr, bool backward_, double mean_row, int lanes) {
+    backward = backward_ ? 1 : 0;
+    nlev = (int)fwd_lvlptr.size() - 1;
+    n = nlev > 0 ? fwd_lvlptr[nlev] : 0;
+    // wavefronts in sweep order, as (begin, end) row ranges
+    std::vector<std::pair<int, int>> wave(nlev);
+    for (int w = 0; w < nlev; ++w) {
+      const int src = backward ? nlev - 1 - w : w;
+      wave[w] = {fwd_lvlptr[src], fwd_lvlptr[src + 1]};
+    }
+    std::vector<int> h_rows((size_t)n);
+    h_lvlptr.assign(nlev + 1, 0);
+    {
+      size_t o = 0;
+      for (int w = 0; w < nlev; ++w) {
+        for (int r = wave[w].first; r < wave[w].second; ++r) h_rows[o++] = r;
+        h_lvlptr[w + 1] = (int)o;
+      }
+    }
+    rows = dev_upload(h_rows);
+    lvlptr = dev_upload(h_lvlptr);
+    // group runs of narrow wavefronts into single-CTA items (fallback mode)
     const int narrow = 4 * (kCtaThreads / lanes);  // <= 4 passes of one CTA
     int l = 0;
     while (l < nlev) {
@@ -360,42 +418,28 @@ struct DevSchedule {
         ++l;
       }
     }
-    // ---- dataflow layout ----
-    const double mean = n ? (double)w.nnz() / (double)n : 0.0;
+    // ---- dataflow tasks ----
     df_lanes = 1;
-    while (df_lanes < 32 && kGsPrefetch * df_lanes < (mean <= kGsPrefetch ? mean : 1.25 * mean)) df_lanes *= 2;
+    while (df_lanes < 32 && kGsPrefetch * df_lanes < (mean_row <= kGsPrefetch ? mean_row : 1.25 * mean_row)) df_lanes *= 2;
     df_lanes = env_int("B200AMG_GS_LANES", df_lanes);
     df_threads = env_int("B200AMG_GS_THREADS", 128) == 256 ? 256 : 128;
     const int R = df_threads / df_lanes;
     std::vector<int4> tk;
-    std::vector<int> wn(std::max(nlev, 1), 0);
-    for (int lv = 0; lv < nlev; ++lv)
-      for (int p = h_lvlptr[lv]; p < h_lvlptr[lv + 1]; p += R) {
-        tk.push_back(make_int4(p, std::min(R, h_lvlptr[lv + 1] - p), lv, 0));
-        wn[lv]++;
-      }
-    for (int4& t : tk) t.w = t.z > 0 ? wn[t.z - 1] : 0;
-    std::vector<int> pp(n + 1, 0), pc((size_t)w.nnz());
-    std::vector<double> pv((size_t)w.nnz());
-    for (int64_t p = 0; p < n; ++p) pp[p + 1] = pp[p] + (w.ptr[h.rows[p] + 1] - w.ptr[h.rows[p]]);
-    for (int64_t p = 0; p < n; ++p) {
-      const int r = h.rows[p];
-      std::copy(w.idx.begin() + w.ptr[r], w.idx.begin() + w.ptr[r + 1], pc.begin() + pp[p]);
-      std::copy(w.val.begin() + w.ptr[r], w.val.begin() + w.ptr[r + 1], pv.begin() + pp[p]);
+    int prev = 0;
+    for (int w = 0; w < nlev; ++w) {
+      int cnt = 0;
+      for (int p = wave[w].first; p < wave[w].second; p += R, ++cnt)
+        tk.push_back(make_int4(p, std::min(R, wave[w].second - p), w, prev));
+      prev = cnt;
     }
     ntasks = (int)tk.size();
     tasks = dev_upload(tk);
-    wave_ntasks = dev_upload(wn);
     counters = dev_alloc<unsigned>((int64_t)(nlev + 2) * kGsCounterStride);
-    pptr = dev_upload(pp);
-    pcol = dev_upload(pc, 8);
-    pval = dev_upload(pv, 8);
     built = true;
   }
   void release() {
-    cudaFree(rows); cudaFree(lvlptr); cudaFree(tasks); cudaFree(wave_ntasks); cudaFree(counters);
-    cudaFree(pptr); cudaFree(pcol); cudaFree(pval);
-    rows = lvlptr = nullptr; tasks = nullptr; wave_ntasks = nullptr; counters = nullptr; pptr = pcol = nullptr; pval = nullptr;
+    cudaFree(rows); cudaFree(lvlptr); cudaFree(tasks); cudaFree(counters);
+    rows = lvlptr = nullptr; tasks = nullptr; counters = nullptr;
     built = false;
   }
 };
@@ -416,6 +460,7 @@ static SmootherCfg to_cfg(const b200amg_smoother_t* s) {
 }
 
 // A matrix prepared for relaxation: the rows the smoother walks + wavefront schedules + diagonal.
+// When a Gauss-Seidel / SOR sweep is requested the level is renumbered into wavefront order (perm).
 struct SmootherMatrix {
   DevCsr A;      // true A by rows
   DevCsr At;     // rows of A' (== the reference's CSC columns); aliases A when A is bit-symmetric
@@ -424,19 +469,53 @@ struct SmootherMatrix {
   DevSchedule fwd, bwd;
   double* diag = nullptr;   // diagonal of the walked matrix (same for A and A')
   int64_t n = 0;
+  HostPerm perm;            // identity unless a sweep smoother renumbered the level
+  int *d_new_of_old = nullptr, *d_old_of_new = nullptr;
+  // mailbox sweep (stream.cuh: gs_mail_kernel): only for structurally symmetric patterns
+  int* d_fwd_lvlptr = nullptr;   // forward wavefront boundaries (single-CTA sweep)
+  int nlev = 0;
+  bool pattern_symmetric = false;
+  uint4* mail = nullptr;
+  unsigned* mail_ctl = nullptr;
   const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
 
-  // hA_t: rows of A' (the staged CSC); need_gs: build wavefront schedules
-  void build(const HostCsr& hAt, int symmetry_, bool need_fwd, bool need_bwd, bool need_true_A) {
+  // hAt_in: rows of A' (the staged CSC)
+  void build(const HostCsr& hAt_in, int symmetry_, bool need_fwd, bool need_bwd, bool need_true_A) {
     symmetry = symmetry_;
-    n = hAt.nrows;
-    HostCsr hA = transpose(hAt);
-    symmetric_bits = bit_equal(hA, hAt);
-    At.upload(hAt);
+    n = hAt_in.nrows;
+    HostCsr hA_in = transpose(hAt_in);
+    symmetric_bits = bit_equal(hA_in, hAt_in);
+    pattern_symmetric = symmetric_bits || (hA_in.ptr == hAt_in.ptr && hA_in.idx == hAt_in.idx);
+    std::vector<int> lvlptr;
+    HostCsr hAt_p, hA_p;
+    const HostCsr* hAt = &hAt_in;
+    const HostCsr* hA = &hA_in;
+    if ((need_fwd || need_bwd) && n > 0) {
+      const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
+      const HostCsr& wt0 = symmetric_bits ? w0 : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA_in : hAt_in);
+      int nlev = 0;
+      std::vector<int> level = wavefront_levels(w0, wt0, &nlev);
+      lvlptr.assign(nlev + 1, 0);
+      for (int64_t i = 0; i < n; ++i) lvlptr[level[i] + 1]++;
+      for (int l = 0; l < nlev; ++l) lvlptr[l + 1] += lvlptr[l];
+      perm.old_of_new.resize(n);
+      perm.new_of_old.resize(n);
+      std::vector<int> next(lvlptr.begin(), lvlptr.end() - 1);
+      for (int64_t i = 0; i < n; ++i) {   // ascending old index inside a wavefront
+        const int q = next[level[i]]++;
+        perm.old_of_new[q] = (int)i;
+        perm.new_of_old[i] = q;
+      }
+      hAt_p = permute_sym(hAt_in, perm);
+      hAt = &hAt_p;
+      if (!symmetric_bits) { hA_p = permute_sym(hA_in, perm); hA = &hA_p; } else hA = &hAt_p;
+      d_new_of_old = dev_upload(perm.new_of_old);
+      d_old_of_new = dev_upload(perm.old_of_new);
+    }
+    At.upload(*hAt);
     if (symmetric_bits) A.alias(At);
-    else if (need_true_A || symmetry == B200AMG_SYMMETRY_NONE) A.upload(hA);
-    const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt : hA;
-    const HostCsr& wt = symmetric_bits ? w : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA : hAt);
+    else if (need_true_A || symmetry == B200AMG_SYMMETRY_NONE) A.upload(*hA);
+    const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA;
     std::vector<double> d(n, 0.0);
     for (int64_t i = 0; i < n; ++i)
       for (int k = w.ptr[i]; k < w.ptr[i + 1]; ++k)
@@ -444,15 +523,34 @@ struct SmootherMatrix {
     diag = dev_upload(d);
     if (symmetry == B200AMG_SYMMETRY_NONE && (need_fwd || need_bwd)) {
       // DiagonalIndices(A): SingularException on a missing / zero diagonal  (smoother.jl:233-248)
+      int64_t bad = -1;   // the reference reports the first (lowest) column without a usable diagonal
       for (int64_t i = 0; i < n; ++i)
-        REQUIRE(d[i] != 0.0, B200AMG_ERR_SINGULAR, "SingularException(%lld)", (long long)(i + 1));
+        if (d[i] == 0.0) {
+          const int64_t old = perm.identity() ? i : perm.old_of_new[i];
+          if (bad < 0 || old < bad) bad = old;
+        }
+      REQUIRE(bad < 0, B200AMG_ERR_SINGULAR, "SingularException(%lld)", (long long)(bad + 1));
     }
-    if (need_fwd) fwd.upload(build_schedule(w, wt, true), w, walked().lanes);
-    if (need_bwd) bwd.upload(build_schedule(w, wt, false), w, walked().lanes);
+    const double mean = n ? (double)w.nnz() / (double)n : 0.0;
+    if (need_fwd) fwd.upload(lvlptr, false, mean, walked().lanes);
+    if (need_bwd) bwd.upload(lvlptr, true, mean, walked().lanes);
+    if ((need_fwd || need_bwd) && n > 0) {
+      d_fwd_lvlptr = dev_upload(lvlptr, 8);
+      nlev = (int)lvlptr.size() - 1;
+    }
+    if ((need_fwd || need_bwd) && pattern_symmetric && n > 0) {
+      mail = dev_alloc<uint4>(n + 8);
+      CUDA_OK(cudaMemset(mail, 0, sizeof(uint4) * (size_t)(n + 8)));
+      const int64_t words = (int64_t)(lvlptr.size() + 4) * kGsCounterStride;
+      mail_ctl = dev_alloc<unsigned>(words);
+      CUDA_OK(cudaMemset(mail_ctl, 0, sizeof(unsigned) * (size_t)words));
+    }
   }
   void release() {
     A.release(); At.release(); fwd.release(); bwd.release();
-    cudaFree(diag); diag = nullptr;
+    cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr);
+    d_fwd_lvlptr = nullptr;
+    diag = nullptr; d_new_of_old = d_old_of_new = nullptr; mail = nullptr; mail_ctl = nullptr;
   }
 };
 
@@ -469,6 +567,9 @@ struct Level {
   bool remote = false;            // this rank holds no device data for the level (rank != 0 of a partition)
   SmootherMatrix M;
   DevCsr P, R;
+  // P and R wait on the host until the NEXT level's numbering is known (add_level / set_coarse)
+  HostCsr pendP, pendR;
+  bool pending = false;
   SmootherCfg pre, post;
   double *res = nullptr, *coarse_x = nullptr, *coarse_b = nullptr, *temp = nullptr;
 };
@@ -527,15 +628,22 @@ struct b200amg_hierarchy {
   cudaGraphExec_t resnorm_graph = nullptr;
   bool use_graphs = true;
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
+  int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
+  int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
+  int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
   int gs_acquire = 0;     // consumer-side acquire of the dataflow sweep: 0 none (see stream.cuh), 1 ld.acquire, 2 fence
   unsigned long long* gs_debug = nullptr;   // 8 timestamps per task of the last dataflow sweep (diagnostics)
-  int gs_mode = 1;        // 1: persistent dataflow sweep, 0: one launch per wavefront (fallback / A-B)
+  int gs_mode = 2;        // 2: per-row mailbox sweep (symmetric patterns; else 1), 1: wavefront-counter dataflow sweep,
+                          // 0: one launch per wavefront (fallback / A-B)
   bool finalized = false;
   bool capturing = false;
   int64_t launches = 0;       // kernels launched (graph replays add their node counts)
   int64_t collectives = 0;    // NCCL groups / collectives enqueued (partitioned handles)
   int64_t capture_count = 0;  // kernels recorded into the graph being captured
+  // staging for renumbered vectors crossing the ABI
+  double* io_tmp = nullptr;
+  int64_t io_cap = 0;
   // L2 flush buffer for time_kernel
   void* flush = nullptr;
   size_t flush_bytes = 0;
@@ -662,30 +770,112 @@ static int gs_dataflow_ctas() {   // co-resident CTAs of the persistent dataflow
   return cached;
 }
 template <int T, int BS>
-static void launch_dataflow_T(H* h, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+static void launch_dataflow_T(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS>());
   CUDA_OK(cudaMemsetAsync(sc.counters, 0, sizeof(unsigned) * (size_t)(sc.nlev + 2) * kGsCounterStride, h->stream));
-  gs_dataflow_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.wave_ntasks, sc.counters, sc.rows, sc.pptr, sc.pcol,
-                                                       sc.pval, x, b, w, sor, h->gs_acquire, h->opaque_zero, h->gs_debug);
+  gs_dataflow_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
+                                                       sc.backward, h->gs_acquire, h->opaque_zero, h->gs_debug);
   count_launch(h);
 }
-static void launch_dataflow(H* h, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+static void launch_dataflow(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   if (sc.ntasks == 0) return;
 #define B200AMG_DF_CASE(TT)                                                    \
   case TT:                                                                     \
-    if (sc.df_threads == 128) launch_dataflow_T<TT, 128>(h, sc, x, b, w, sor); \
-    else launch_dataflow_T<TT, 256>(h, sc, x, b, w, sor);                      \
+    if (sc.df_threads == 128) launch_dataflow_T<TT, 128>(h, A, sc, x, b, w, sor); \
+    else launch_dataflow_T<TT, 256>(h, A, sc, x, b, w, sor);                      \
     break;
   switch (sc.df_lanes) {
     B200AMG_DF_CASE(1) B200AMG_DF_CASE(2) B200AMG_DF_CASE(4) B200AMG_DF_CASE(8) B200AMG_DF_CASE(16)
     default:
-      if (sc.df_threads == 128) launch_dataflow_T<32, 128>(h, sc, x, b, w, sor);
-      else launch_dataflow_T<32, 256>(h, sc, x, b, w, sor);
+      if (sc.df_threads == 128) launch_dataflow_T<32, 128>(h, A, sc, x, b, w, sor);
+      else launch_dataflow_T<32, 256>(h, A, sc, x, b, w, sor);
   }
 #undef B200AMG_DF_CASE
 }
-static void launch_sweep(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
-  if (h->gs_mode == 1) { launch_dataflow(h, sc, x, b, w, sor); return; }
+template <int T, int BS>
+static int gs_mail_ctas() {
+  static int cached = 0;
+  if (!cached) {
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_mail_kernel<T, BS>, BS, 0));
+    cached = std::max(1, per_sm) * kNumSM;
+  }
+  return cached;
+}
+template <int T, int BS>
+static void launch_mail_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                          int sor) {
+  const int ctas = std::min(sc.ntasks, gs_mail_ctas<T, BS>());
+  gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(M.mail_ctl);
+  count_launch(h);
+  gs_mail_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor,
+                                                   sc.backward, h->opaque_zero, h->gs_poll_sleep, h->gs_gate_sleep);
+  count_launch(h);
+}
+static void launch_mail(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                        int sor) {
+  if (sc.ntasks == 0) return;
+#define B200AMG_ML_CASE(TT)                                                       \
+  case TT:                                                                        \
+    if (sc.df_threads == 128) launch_mail_T<TT, 128>(h, M, A, sc, x, b, w, sor);  \
+    else launch_mail_T<TT, 256>(h, M, A, sc, x, b, w, sor);                       \
+    break;
+  switch (sc.df_lanes) {
+    B200AMG_ML_CASE(1) B200AMG_ML_CASE(2) B200AMG_ML_CASE(4) B200AMG_ML_CASE(8) B200AMG_ML_CASE(16)
+    default:
+      if (sc.df_threads == 128) launch_mail_T<32, 128>(h, M, A, sc, x, b, w, sor);
+      else launch_mail_T<32, 256>(h, M, A, sc, x, b, w, sor);
+  }
+#undef B200AMG_ML_CASE
+}
+constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
+template <int T, bool XS>
+static void gs_cta_set_attr() {
+  CUDA_OK(cudaFuncSetAttribute(gs_cta_kernel<T, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)(kStages * sizeof(GsCtaStage) + (XS ? kGsCtaXsRows * sizeof(double) : 0))));
+}
+static void gs_cta_kernels_init() {
+  gs_cta_set_attr<1, false>(); gs_cta_set_attr<2, false>(); gs_cta_set_attr<4, false>(); gs_cta_set_attr<8, false>();
+  gs_cta_set_attr<16, false>(); gs_cta_set_attr<32, false>();
+  gs_cta_set_attr<1, true>(); gs_cta_set_attr<2, true>(); gs_cta_set_attr<4, true>(); gs_cta_set_attr<8, true>();
+  gs_cta_set_attr<16, true>(); gs_cta_set_attr<32, true>();
+}
+template <int T>
+static void launch_gs_cta_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                            int sor) {
+  const bool xs = M.n <= kGsCtaXsRows;
+  const size_t smem = kStages * sizeof(GsCtaStage) + (xs ? (size_t)M.n * sizeof(double) : 0);
+  if (xs)
+    gs_cta_kernel<T, true><<<1, kGsCtaThreads, smem, h->stream>>>((int)M.n, A.ntiles, A.meta, A.ptr, A.idx, A.val, M.d_fwd_lvlptr, M.nlev,
+                                                                 x, b, w, sor, sc.backward);
+  else
+    gs_cta_kernel<T, false><<<1, kGsCtaThreads, smem, h->stream>>>((int)M.n, A.ntiles, A.meta, A.ptr, A.idx, A.val, M.d_fwd_lvlptr,
+                                                                  M.nlev, x, b, w, sor, sc.backward);
+  count_launch(h);
+}
+static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                          int sor) {
+  const double mean = M.n ? (double)A.nnz / (double)M.n : 0.0;
+  int T = 1;
+  while (T < 32 && T < mean) T *= 2;
+  switch (T) {
+    case 1: launch_gs_cta_T<1>(h, M, A, sc, x, b, w, sor); break;
+    case 2: launch_gs_cta_T<2>(h, M, A, sc, x, b, w, sor); break;
+    case 4: launch_gs_cta_T<4>(h, M, A, sc, x, b, w, sor); break;
+    case 8: launch_gs_cta_T<8>(h, M, A, sc, x, b, w, sor); break;
+    case 16: launch_gs_cta_T<16>(h, M, A, sc, x, b, w, sor); break;
+    default: launch_gs_cta_T<32>(h, M, A, sc, x, b, w, sor); break;
+  }
+}
+static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  const DevCsr& A = M.walked();
+  // Which sweep: measured on B200 (tools/tune_kernels.py, profiles/): one CTA wins while x fits in shared
+  // memory (~1 us per wavefront); the per-row mailbox sweep wins on wide wavefronts (>= ~1000 rows); the
+  // wavefront-counter sweep in between.
+  if (h->gs_mode >= 1 && M.n <= h->gs_cta_rows && A.ntiles > 0 && M.d_fwd_lvlptr) { launch_gs_cta(h, M, A, sc, x, b, w, sor); return; }
+  const bool wide = sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width;
+  if (h->gs_mode == 2 && M.mail && wide) { launch_mail(h, M, A, sc, x, b, w, sor); return; }
+  if (h->gs_mode >= 1) { launch_dataflow(h, A, sc, x, b, w, sor); return; }
   switch (A.lanes) {
     case 2: launch_sweep_T<2>(h, A, sc, x, b, w, sor); break;
     case 4: launch_sweep_T<4>(h, A, sc, x, b, w, sor); break;
@@ -723,8 +913,8 @@ static void smooth(H* h, const SmootherMatrix& M, const SmootherCfg& c, double* 
   }
   const int sor = c.kind == B200AMG_SMOOTHER_SOR;
   for (int it = 0; it < c.iter; ++it) {
-    if (c.sweep == 1 || c.sweep == 3) launch_sweep(h, A, M.fwd, x, b, c.omega, sor);
-    if (c.sweep == 2 || c.sweep == 3) launch_sweep(h, A, M.bwd, x, b, c.omega, sor);
+    if (c.sweep == 1 || c.sweep == 3) launch_sweep(h, M, M.fwd, x, b, c.omega, sor);
+    if (c.sweep == 2 || c.sweep == 3) launch_sweep(h, M, M.bwd, x, b, c.omega, sor);
   }
 }
 
@@ -812,8 +1002,8 @@ static int64_t estimate_launches(H* h, int cycle, int lvl) {
     if (c.kind == 0) return 0;
     if (c.kind == B200AMG_SMOOTHER_JACOBI) return c.iter + 1;
     int64_t per = 0;
-    if (c.sweep == 1 || c.sweep == 3) per += h->gs_mode == 1 ? 1 : (int64_t)L.M.fwd.items.size();
-    if (c.sweep == 2 || c.sweep == 3) per += h->gs_mode == 1 ? 1 : (int64_t)L.M.bwd.items.size();
+    if (c.sweep == 1 || c.sweep == 3) per += h->gs_mode >= 1 ? 2 : (int64_t)L.M.fwd.items.size();
+    if (c.sweep == 2 || c.sweep == 3) per += h->gs_mode >= 1 ? 2 : (int64_t)L.M.bwd.items.size();
     return per * c.iter;
   };
   int64_t n = sm(L.pre) + sm(L.post) + 4;
@@ -1034,6 +1224,61 @@ static void check_ready(H* h) {
   REQUIRE(h->finalized, B200AMG_ERR_STATE, "hierarchy not finalized (call b200amg_finalize first)");
   set_device(h);
 }
+// ---- vectors cross the ABI in the caller's (reference) numbering; renumbered levels permute on the way ----
+__global__ void __launch_bounds__(kThreads) gather_kernel(int64_t n, const int* __restrict__ idx, const double* __restrict__ src,
+                                                          double* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+static double* io_scratch(H* h, int64_t n) {
+  if (h->io_cap < n) {
+    cudaFree(h->io_tmp);
+    h->io_tmp = nullptr;
+    h->io_cap = 0;
+    h->io_tmp = dev_alloc<double>(n + 8);
+    h->io_cap = n;
+  }
+  return h->io_tmp;
+}
+// dst (device, level numbering) <- src (caller, natural numbering); M == nullptr or identity: plain copy
+static void vec_in(H* h, const SmootherMatrix* M, double* dst, const double* src, int64_t n, int memkind) {
+  if (n == 0) return;
+  const cudaMemcpyKind kind = memkind == B200AMG_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+  if (!M || M->perm.identity()) {
+    CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, kind, h->stream));
+    return;
+  }
+  const double* dsrc = src;
+  if (memkind == B200AMG_MEM_HOST) {
+    double* tmp = io_scratch(h, n);
+    CUDA_OK(cudaMemcpyAsync(tmp, src, sizeof(double) * (size_t)n, kind, h->stream));
+    dsrc = tmp;
+  }
+  gather_kernel<<<grid_for(n), kThreads, 0, h->stream>>>(n, M->d_old_of_new, dsrc, dst);   // dst[p] = src[old_of_new[p]]
+  count_launch(h);
+}
+// dst (caller, natural numbering) <- src (device, level numbering)
+static void vec_out(H* h, const SmootherMatrix* M, double* dst, const double* src, int64_t n, int memkind) {
+  if (n == 0) return;
+  const cudaMemcpyKind kind = memkind == B200AMG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (!M || M->perm.identity()) {
+    CUDA_OK(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n, kind, h->stream));
+    return;
+  }
+  if (memkind == B200AMG_MEM_HOST) {
+    double* tmp = io_scratch(h, n);
+    gather_kernel<<<grid_for(n), kThreads, 0, h->stream>>>(n, M->d_new_of_old, src, tmp);   // tmp[i] = src[new_of_old[i]]
+    count_launch(h);
+    CUDA_OK(cudaMemcpyAsync(dst, tmp, sizeof(double) * (size_t)n, kind, h->stream));
+  } else {
+    gather_kernel<<<grid_for(n), kThreads, 0, h->stream>>>(n, M->d_new_of_old, src, dst);
+    count_launch(h);
+  }
+}
+static const SmootherMatrix* level_numbering(H* h, int level) {   // nullptr: natural numbering
+  return level >= 0 && level < (int)h->levels.size() && !h->levels[level]->remote ? &h->levels[level]->M : nullptr;
+}
+
 static void check_not_partitioned(H* h, const char* what) {
   REQUIRE(!h->part, B200AMG_ERR_UNSUPPORTED, "%s is not available on a row-partitioned handle (use solve / cycle / precond)", what);
 }
@@ -1050,7 +1295,7 @@ static void from_dev(H* h, double* dst, const double* src, int64_t n, int memkin
 // scratch device vector big enough for any level-sized temporary used by the entry points
 struct Scratch {
   double* p = nullptr;
-  explicit Scratch(int64_t n) { p = dev_alloc<double>(n); }
+  explicit Scratch(int64_t n) { p = dev_alloc<double>(n + 8); }   // +8: TMA row-slice copies round up
   ~Scratch() { cudaFree(p); }
 };
 
@@ -1076,14 +1321,33 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   CUDA_OK(cudaSetDevice(device));
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   stream_kernels_init();
+  gs_cta_kernels_init();
   h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
-  h->gs_mode = env_int("B200AMG_GS_MODE", 1);
+  h->gs_mode = env_int("B200AMG_GS_MODE", 2);
   h->gs_acquire = env_int("B200AMG_GS_ACQUIRE", 0);
+  h->gs_cta_rows = env_int("B200AMG_GS_CTA_ROWS", 12288);
+  h->gs_mail_min_width = env_int("B200AMG_GS_MAIL_MIN_WIDTH", 1024);
+  h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
+  h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
   CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * 16));
   *out = h.release();
   API_END
+}
+
+// upload P and R of `prev` once the numbering of the level below it is known (nullptr / identity: unchanged)
+static void finish_transfer_operators(Level& prev, const HostPerm* coarse) {
+  if (!prev.pending) return;
+  if (coarse && !coarse->identity()) {
+    map_cols(prev.pendP, *coarse);
+    prev.pendR = permute_rows(prev.pendR, *coarse);
+  }
+  prev.P.upload(prev.pendP);
+  prev.R.upload(prev.pendR);
+  prev.pendP = HostCsr();
+  prev.pendR = HostCsr();
+  prev.pending = false;
 }
 
 // level 1 of a partitioned hierarchy: local blocks, halo plan, local vectors
@@ -1165,15 +1429,21 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
     } else if (remote) {
       L->remote = true;
     } else {
-      L->P.upload(hP);
-      L->R.upload(hR);
       L->M.build(hAt, symmetry, cfg_needs_fwd(L->pre) || cfg_needs_fwd(L->post), cfg_needs_bwd(L->pre) || cfg_needs_bwd(L->post), true);
+      REQUIRE(!(h->part && h->levels.size() == 1 && !L->M.perm.identity()), B200AMG_ERR_UNSUPPORTED,
+              "the level below a partitioned fine level must use Jacobi smoothing (its numbering is shared with the other ranks)");
+      // this level's numbering: rows of P, columns of R now; the coarse side when the next level arrives
+      L->pendP = permute_rows(hP, L->M.perm);
+      map_cols(hR, L->M.perm);
+      L->pendR = std::move(hR);
+      L->pending = true;
       L->res = dev_alloc<double>(L->n + 8);
       L->temp = dev_alloc<double>(L->n + 8);
       L->coarse_x = dev_alloc<double>(L->nc + 8);
       L->coarse_b = dev_alloc<double>(L->nc + 8);
     }
   }
+  if (!h->levels.empty()) finish_transfer_operators(*h->levels.back(), L->remote ? nullptr : &L->M.perm);
   h->levels.push_back(std::move(L));
   API_END
 }
@@ -1191,6 +1461,7 @@ int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int
             (long long)n, (long long)h->levels.back()->nc);
   set_device(h);
   REQUIRE(h->world == 1 || !h->levels.empty(), B200AMG_ERR_UNSUPPORTED, "a partitioned hierarchy needs at least one level");
+  if (!h->levels.empty()) finish_transfer_operators(*h->levels.back(), nullptr);   // the coarsest level keeps its numbering
   h->nfinal = n;
   if (h->world == 1 || h->rank == 0) {
     HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
@@ -1306,7 +1577,7 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
   cudaFree(h->partial); cudaFree(h->scalars); cudaFreeHost(h->h_scalars);
-  cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush);
+  cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush); cudaFree(h->io_tmp);
   for (cudaEvent_t e : h->res_events) cudaEventDestroy(e);
   for (int c = 0; c < 3; ++c)
     if (h->cycle_graph[c]) cudaGraphExecDestroy(h->cycle_graph[c]);
@@ -1329,8 +1600,8 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
     part_load(h, h->part->b, b, memkind);
     part_load(h, h->part->x, x, memkind);
   } else {
-    to_dev(h, h->b0, b, n, memkind);
-    to_dev(h, h->x0, x, n, memkind);
+    vec_in(h, level_numbering(h, 0), h->b0, b, n, memkind);
+    vec_in(h, level_numbering(h, 0), h->x0, x, n, memkind);
   }
   int nr = 0;
   h->res_events_used = 0;
@@ -1369,7 +1640,7 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
     itr += 1;
   }
   if (h->part) part_store(h, x, h->part->x, memkind);
-  else from_dev(h, x, h->x0, n, memkind);
+  else vec_out(h, level_numbering(h, 0), x, h->x0, n, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   if (nres) *nres = nr;
   if (iters) *iters = itr - 1;
@@ -1387,10 +1658,10 @@ int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cy
     run_cycle(h, cycle);
     part_store(h, x, h->part->x, memkind);
   } else {
-    to_dev(h, h->b0, b, h->n0, memkind);
-    to_dev(h, h->x0, x, h->n0, memkind);
+    vec_in(h, level_numbering(h, 0), h->b0, b, h->n0, memkind);
+    vec_in(h, level_numbering(h, 0), h->x0, x, h->n0, memkind);
     run_cycle(h, cycle);
-    from_dev(h, x, h->x0, h->n0, memkind);
+    vec_out(h, level_numbering(h, 0), x, h->x0, h->n0, memkind);
   }
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
@@ -1412,11 +1683,11 @@ int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t 
     CUDA_OK(cudaStreamSynchronize(h->stream));
     return B200AMG_OK;
   }
-  to_dev(h, h->b0, b, h->n0, memkind);
+  vec_in(h, level_numbering(h, 0), h->b0, b, h->n0, memkind);
   if (init_zero) CUDA_OK(cudaMemsetAsync(h->x0, 0, sizeof(double) * (size_t)std::max<int64_t>(h->n0, 1), h->stream));
   else CUDA_OK(cudaMemcpyAsync(h->x0, h->b0, sizeof(double) * h->n0, cudaMemcpyDeviceToDevice, h->stream));
   run_cycle(h, cycle);
-  from_dev(h, x, h->x0, h->n0, memkind);
+  vec_out(h, level_numbering(h, 0), x, h->x0, h->n0, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1429,10 +1700,10 @@ int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double*
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   Level& L = *h->levels[level];
   Scratch sx(L.n), sb(L.n);
-  to_dev(h, sx.p, x, L.n, memkind);
-  to_dev(h, sb.p, b, L.n, memkind);
+  vec_in(h, &L.M, sx.p, x, L.n, memkind);
+  vec_in(h, &L.M, sb.p, b, L.n, memkind);
   smooth(h, L.M, which == B200AMG_PRE ? L.pre : L.post, sx.p, sb.p, L.temp, false);
-  from_dev(h, x, sx.p, L.n, memkind);
+  vec_out(h, &L.M, x, sx.p, L.n, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1444,17 +1715,22 @@ int32_t b200amg_apply(b200amg_handle_t h, int32_t level, int32_t op, double* y, 
   REQUIRE(y && x, B200AMG_ERR_BAD_ARG, "null vector");
   const int nl = (int)h->levels.size();
   const DevCsr* A = nullptr;
+  const SmootherMatrix *num_in = nullptr, *num_out = nullptr;   // numbering of the input / output vector
   if (level == nl && op == B200AMG_OP_A) A = &h->finalA;
   else {
     REQUIRE(level >= 0 && level < nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
     Level& L = *h->levels[level];
     A = op == B200AMG_OP_A ? &L.M.A : op == B200AMG_OP_P ? &L.P : op == B200AMG_OP_R ? &L.R : nullptr;
     REQUIRE(A, B200AMG_ERR_BAD_ARG, "unknown operator %d", op);
+    const SmootherMatrix* fine = level_numbering(h, level);
+    const SmootherMatrix* coarse = level_numbering(h, level + 1);
+    num_in = op == B200AMG_OP_A ? fine : op == B200AMG_OP_P ? coarse : fine;
+    num_out = op == B200AMG_OP_A ? fine : op == B200AMG_OP_P ? fine : coarse;
   }
   Scratch sx(A->ncols), sy(A->nrows);
-  to_dev(h, sx.p, x, A->ncols, memkind);
+  vec_in(h, num_in, sx.p, x, A->ncols, memkind);
   spmv(h, *A, sx.p, sy.p);
-  from_dev(h, y, sy.p, A->nrows, memkind);
+  vec_out(h, num_out, y, sy.p, A->nrows, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1468,10 +1744,11 @@ int32_t b200amg_residual(b200amg_handle_t h, int32_t level, double* r, const dou
   REQUIRE(level >= 0 && level <= nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
   const DevCsr& A = level == nl ? h->finalA : h->levels[level]->M.A;
   Scratch sx(A.ncols), sb(A.nrows), sr(A.nrows);
-  to_dev(h, sx.p, x, A.ncols, memkind);
-  to_dev(h, sb.p, b, A.nrows, memkind);
+  const SmootherMatrix* num = level_numbering(h, level);
+  vec_in(h, num, sx.p, x, A.ncols, memkind);
+  vec_in(h, num, sb.p, b, A.nrows, memkind);
   residual(h, A, sx.p, sb.p, sr.p);
-  from_dev(h, r, sr.p, A.nrows, memkind);
+  vec_out(h, num, r, sr.p, A.nrows, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1519,7 +1796,7 @@ int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycl
   const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
   if (!h->pcg_u) { h->pcg_u = dev_alloc<double>(n); h->pcg_q = dev_alloc<double>(n); h->pcg_x = dev_alloc<double>(n); }
   double* S = h->scalars;  // [0] norm [1] rho [2] rho_prev [3] uq
-  to_dev(h, h->b0, b, n, memkind);                                                       // r = b (x starts at zero)
+  vec_in(h, level_numbering(h, 0), h->b0, b, n, memkind);                                 // r = b (x starts at zero)
   CUDA_OK(cudaMemsetAsync(h->pcg_x, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), h->stream));
   CUDA_OK(cudaMemsetAsync(h->pcg_u, 0, sizeof(double) * (size_t)std::max<int64_t>(n, 1), h->stream));
   set_scalar_kernel<<<1, 32, 0, h->stream>>>(S + 1, 1.0);
@@ -1547,7 +1824,7 @@ int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycl
     if (residuals && nr < cap) residuals[nr++] = residual;
     ++it;
   }
-  from_dev(h, x, h->pcg_x, n, memkind);
+  vec_out(h, level_numbering(h, 0), x, h->pcg_x, n, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   if (nres) *nres = nr;
   if (iters) *iters = it;
@@ -1578,9 +1855,9 @@ int32_t b200amg_smoother_create(b200amg_smoother_handle_t* out, int32_t device, 
     s->cfg = to_cfg(config);
     HostCsr hAt = stage_csc_as_rows_of_transpose(A);
     s->M.build(hAt, symmetry, cfg_needs_fwd(s->cfg), cfg_needs_bwd(s->cfg), false);
-    s->x = dev_alloc<double>(A->n);
-    s->b = dev_alloc<double>(A->n);
-    s->temp = dev_alloc<double>(A->n);
+    s->x = dev_alloc<double>(A->n + 8);
+    s->b = dev_alloc<double>(A->n + 8);
+    s->temp = dev_alloc<double>(A->n + 8);
   } catch (...) {
     s->M.release(); cudaFree(s->x); cudaFree(s->b); cudaFree(s->temp);
     b200amg_destroy(hh);
@@ -1595,10 +1872,10 @@ int32_t b200amg_smoother_apply(b200amg_smoother_handle_t s, double* x, const dou
   REQUIRE(s && x && b, B200AMG_ERR_BAD_ARG, "null argument");
   H* h = s->h;
   set_device(h);
-  to_dev(h, s->x, x, s->M.n, memkind);
-  to_dev(h, s->b, b, s->M.n, memkind);
+  vec_in(h, &s->M, s->x, x, s->M.n, memkind);
+  vec_in(h, &s->M, s->b, b, s->M.n, memkind);
   smooth(h, s->M, s->cfg, s->x, s->b, s->temp, false);
-  from_dev(h, x, s->x, s->M.n, memkind);
+  vec_out(h, &s->M, x, s->x, s->M.n, memkind);
   CUDA_OK(cudaStreamSynchronize(h->stream));
   API_END
 }
@@ -1734,6 +2011,9 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_STREAM_CHUNK: h->stream_chunk = (int)value; break;
     case B200AMG_OPT_GS_MODE: h->gs_mode = (int)value; break;
     case B200AMG_OPT_GS_ACQUIRE: h->gs_acquire = (int)value; break;
+    case B200AMG_OPT_GS_POLL_SLEEP: h->gs_poll_sleep = (int)value; break;
+    case B200AMG_OPT_GS_CTA_ROWS: h->gs_cta_rows = (int64_t)value; break;
+    case B200AMG_OPT_GS_GATE_SLEEP: h->gs_gate_sleep = (int)value; break;
     default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown option %d", option);
   }
   API_END
@@ -1771,7 +2051,7 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   const int sor = L.pre.kind == B200AMG_SMOOTHER_SOR;
   double* x = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
   const double* b = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
-  launch_dataflow(h, sc, x, b, L.pre.omega, sor);
+  launch_dataflow(h, L.M.walked(), sc, x, b, L.pre.omega, sor);
   h->gs_debug = nullptr;
   CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -195,39 +195,38 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
 // Gauss-Seidel / SOR as a DATAFLOW sweep (exact lexicographic semantics of gs! smoother.jl:73-90 and
 // sor_step! :205-221).
 //
-// The rows are stored a second time in wavefront order (level schedule of the symmetrised
-// pattern: rows of one wavefront are mutually independent; every earlier-ordered neighbour sits in
-// an earlier wavefront, every later-ordered one in a later wavefront).  The sweep is ONE persistent
-// kernel: CTAs claim TASKS (<= 256/T consecutive rows of one wavefront) in schedule order from a
-// ticket counter, prefetch everything that does not depend on x (row pointers, column indices,
-// values, b) into registers, and only then wait until the previous wavefront's completion counter
-// is full (one acquire-poll per CTA), gather x through L2 (ld.cg: other SMs wrote it), relax and
-// publish with a release-increment of their own wavefront's counter.  Dependency latency per
-// wavefront is one L2 round trip instead of a kernel launch or a grid barrier, and the matrix
-// streams of later wavefronts are already in flight while earlier ones resolve.
+// Levels that are relaxed by Gauss-Seidel / SOR are RENUMBERED at upload into wavefront order (level
+// schedule of the symmetrised pattern for the ascending-index sweep: rows of one wavefront are mutually
+// independent, every earlier-ordered neighbour sits in an earlier wavefront, every later-ordered one
+// in a later wavefront; the backward sweep walks the same wavefronts in reverse).  Inside a row the
+// entries keep the reference's order.  A wavefront is then a contiguous row range of the ordinary CSR
+// arrays, neighbouring rows of a wavefront read neighbouring x entries (coalesced), and the sweep is
+// ONE persistent kernel:
+//   * CTAs claim TASKS (<= BS/T consecutive rows of one wavefront) in sweep order from a ticket counter;
+//   * everything that does not depend on this sweep's progress is requested BEFORE waiting: row
+//     pointers, column indices, values, b, and the x entries of LATER-ordered neighbours (nobody
+//     touches those until this task has published);
+//   * one thread polls the previous wavefront's completion counter; then the EARLIER-ordered x
+//     entries are gathered in a single burst straight from L2 (ld.cg: other SMs wrote them), the row is
+//     relaxed, and the task publishes with fence + counter increment.
+// Dependency latency per wavefront is one L2 hand-off instead of a kernel launch or a grid barrier,
+// and the matrix streams of later wavefronts are already in registers while earlier ones resolve.
+// Claiming by ticket makes it deadlock-free for any grid size: a task is only ever held by a resident
+// CTA, and the lowest unfinished task never waits on anything unfinished.
 //
-// Claiming by ticket makes it deadlock-free for any grid size: a task is only ever held by a
-// resident CTA, and the lowest unfinished task never waits on anything unfinished.
-//
-// T = 1: one thread per row, sequential ascending-column accumulation, separate multiply/add
+// T = 1: one thread per row, sequential accumulation in the reference's order, separate multiply/add
 // roundings and a true division -> bit-identical to the reference's sequential sweep.
 // =============================================================================================
-constexpr int kGsThreads = 256;
 constexpr int kGsPrefetch = 8;   // (column, value) pairs a lane holds in registers across the wait
-
 constexpr int kGsCounterStride = 64;   // uints between counters: 256 B apart = different L2 slices, no hot line
+constexpr int kGsFarWaves = 4;   // CTAs this many wavefronts ahead of the front sleep-poll
+
+__device__ double g_gs_zero = 0.0;   // what idle slots of the gather burst read
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   unsigned v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
-}
-__device__ double g_gs_zero = 0.0;   // what padding slots of the gather burst read
-constexpr int kGsFarWaves = 4;   // CTAs this many wavefronts ahead of the front sleep-poll
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   unsigned v;
@@ -237,15 +236,46 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_relaxed_inc(unsigned* p) {
   asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// eight L1-bypassing loads issued back to back (one asm block: NVVM cannot sink them)
+__device__ __forceinline__ void ldcg_burst8(double (&out)[kGsPrefetch], const double* const (&a)[kGsPrefetch]) {
+  static_assert(kGsPrefetch == 8, "the burst is written for 8 slots");
+  asm volatile(
+      "ld.global.cg.f64 %0, [%8];\n\t"
+      "ld.global.cg.f64 %1, [%9];\n\t"
+      "ld.global.cg.f64 %2, [%10];\n\t"
+      "ld.global.cg.f64 %3, [%11];\n\t"
+      "ld.global.cg.f64 %4, [%12];\n\t"
+      "ld.global.cg.f64 %5, [%13];\n\t"
+      "ld.global.cg.f64 %6, [%14];\n\t"
+      "ld.global.cg.f64 %7, [%15];"
+      : "=d"(out[0]), "=d"(out[1]), "=d"(out[2]), "=d"(out[3]), "=d"(out[4]), "=d"(out[5]), "=d"(out[6]), "=d"(out[7])
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
+      : "memory");
+}
+// ptxas sinks each load of a burst down to its first use, and in-order issue then serialises the L2
+// round trips (measured: 1.0 us of a 2.0 us hop).  Folding all results into one run-time zero that
+// every later use depends on pins the whole burst in front of the first wait.
+__device__ __forceinline__ void pin_burst8(double (&v)[kGsPrefetch], int opaque_zero) {
+  int dep = __double2hiint(v[0]);
+#pragma unroll
+  for (int j = 1; j < kGsPrefetch; ++j) dep &= __double2hiint(v[j]);
+  dep &= opaque_zero;
+#pragma unroll
+  for (int j = 0; j < kGsPrefetch; ++j) v[j] = __hiloint2double(__double2hiint(v[j]) | dep, __double2loint(v[j]));
+}
 
-// tasks[t] = {first position in schedule order, rows, wavefront, tasks of the previous wavefront}
+// tasks[t] = {first row, rows, wavefront in sweep order, tasks of the previous wavefront}
 // counters[0] = ticket, counters[(1 + w) * kGsCounterStride] = finished tasks of wavefront w (zeroed before the launch)
 template <int T, int BS>
 __global__ void __launch_bounds__(BS)
-    gs_dataflow_kernel(int ntasks, const int4* __restrict__ tasks, const int* __restrict__ wave_ntasks, unsigned* counters,
-                       const int* __restrict__ perm, const int* __restrict__ pptr, const int* __restrict__ pcol,
-                       const double* __restrict__ pval, double* x, const double* __restrict__ b, double omega, int sor,
-                       int acquire_mode, int opaque_zero, unsigned long long* dbg) {
+    gs_dataflow_kernel(int ntasks, const int4* __restrict__ tasks, unsigned* counters, const int* __restrict__ rowptr,
+                       const int* __restrict__ col, const double* __restrict__ val, double* x, const double* __restrict__ b,
+                       double omega, int sor, int backward, int acquire_mode, int opaque_zero, unsigned long long* dbg) {
   __shared__ int s_task[2];
   const int tid = threadIdx.x, g = tid / T, lane = tid % T;
   if (tid == 0) s_task[0] = (int)atomicAdd(&counters[0], 1u);
@@ -256,13 +286,12 @@ __global__ void __launch_bounds__(BS)
     const int4 tk = __ldg(tasks + cur);
     if (dbg && tid == 0) dbg[(size_t)cur * 8 + 0] = global_ns();
     const bool active = g < tk.y;
-    int row = -1, ks = 0, ke = 0;
+    const int row = active ? tk.x + g : -1;
+    int ks = 0, ke = 0;
     double bv = 0.0, xold = 0.0;
     if (active) {
-      const int p = tk.x + g;
-      row = __ldg(perm + p);
-      ks = __ldg(pptr + p);
-      ke = __ldg(pptr + p + 1);
+      ks = __ldg(rowptr + row);
+      ke = __ldg(rowptr + row + 1);
       if (lane == 0) {
         bv = __ldg(b + row);
         if (sor) xold = __ldcg(x + row);   // only this row's own update ever writes x[row] during the sweep
@@ -274,10 +303,20 @@ __global__ void __launch_bounds__(BS)
     for (int j = 0; j < kGsPrefetch; ++j) {
       const int k = ks + lane + j * T;
       const bool in = k < ke;
-      c[j] = in ? __ldg(pcol + k) : -1;
-      v[j] = in ? __ldg(pval + k) : 0.0;
+      c[j] = in ? __ldg(col + k) : -1;
+      v[j] = in ? __ldg(val + k) : 0.0;
     }
-    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 1] = global_ns();
+    // later-ordered neighbours keep their old value until this task has published: fetch them now
+    double xl[kGsPrefetch];
+    {
+      const double* a[kGsPrefetch];
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) {
+        const bool later = c[j] >= 0 && (backward ? c[j] < row : c[j] > row);
+        a[j] = later ? x + c[j] : &g_gs_zero;
+      }
+      ldcg_burst8(xl, a);
+    }
     if (tk.z > 0) {
       if (tid == 0) {
         const unsigned need = (unsigned)tk.w;   // tasks of wavefront tk.z - 1
@@ -298,48 +337,31 @@ __global__ void __launch_bounds__(BS)
       __syncthreads();
     }
     if (dbg && tid == 0) dbg[(size_t)cur * 8 + 3] = global_ns();
-    // All gathers of the task leave in one burst (a single asm block: neither NVVM nor ptxas may sink
-    // a load down to its use), so the critical path pays ONE L2 round trip.  Padding slots read a
-    // global zero; the diagonal slot reads x[row] and is skipped below.
-    double xv[kGsPrefetch];
+    // earlier-ordered neighbours: one burst, one L2 round trip on the critical path
+    double xe[kGsPrefetch];
     {
       const double* a[kGsPrefetch];
 #pragma unroll
-      for (int j = 0; j < kGsPrefetch; ++j) a[j] = c[j] >= 0 ? x + c[j] : &g_gs_zero;
-      static_assert(kGsPrefetch == 8, "the burst below is written for 8 slots");
-      asm volatile(
-          "ld.global.cg.f64 %0, [%8];\n\t"
-          "ld.global.cg.f64 %1, [%9];\n\t"
-          "ld.global.cg.f64 %2, [%10];\n\t"
-          "ld.global.cg.f64 %3, [%11];\n\t"
-          "ld.global.cg.f64 %4, [%12];\n\t"
-          "ld.global.cg.f64 %5, [%13];\n\t"
-          "ld.global.cg.f64 %6, [%14];\n\t"
-          "ld.global.cg.f64 %7, [%15];"
-          : "=d"(xv[0]), "=d"(xv[1]), "=d"(xv[2]), "=d"(xv[3]), "=d"(xv[4]), "=d"(xv[5]), "=d"(xv[6]), "=d"(xv[7])
-          : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
-          : "memory");
+      for (int j = 0; j < kGsPrefetch; ++j) {
+        const bool earlier = c[j] >= 0 && (backward ? c[j] > row : c[j] < row);
+        a[j] = earlier ? x + c[j] : &g_gs_zero;
+      }
+      ldcg_burst8(xe, a);
+      pin_burst8(xe, opaque_zero);
     }
-    {
-      // ptxas otherwise sinks each load down to its multiply, and in-order issue then serialises the
-      // eight L2 round trips (measured: 1.0 us of a 2.0 us hop).  Folding all eight results into one
-      // run-time zero that every product depends on pins the loads in front of the first wait.
-      int dep = __double2hiint(xv[0]);
-#pragma unroll
-      for (int j = 1; j < kGsPrefetch; ++j) dep &= __double2hiint(xv[j]);
-      dep &= opaque_zero;
-#pragma unroll
-      for (int j = 0; j < kGsPrefetch; ++j) xv[j] = __hiloint2double(__double2hiint(xv[j]) | dep, __double2loint(xv[j]));
-    }
+    if (dbg && tid == 0) dbg[(size_t)cur * 8 + 1] = global_ns() + (unsigned long long)(__double2loint(xe[0]) & opaque_zero);
     double rsum = 0.0, d = 0.0;
 #pragma unroll
     for (int j = 0; j < kGsPrefetch; ++j) {
       if (c[j] == row && c[j] >= 0) d = v[j];
-      else rsum = __dadd_rn(rsum, __dmul_rn(v[j], xv[j]));   // padding adds an exact +0
+      else {
+        const bool later = c[j] >= 0 && (backward ? c[j] < row : c[j] > row);
+        rsum = __dadd_rn(rsum, __dmul_rn(v[j], later ? xl[j] : xe[j]));   // idle slots add an exact +0
+      }
     }
     for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {   // rows longer than T * kGsPrefetch
-      const int cc = __ldg(pcol + k);
-      const double vv = __ldg(pval + k);
+      const int cc = __ldg(col + k);
+      const double vv = __ldg(val + k);
       if (cc == row) d = vv;
       else rsum = __dadd_rn(rsum, __dmul_rn(vv, __ldcg(x + cc)));
     }
@@ -364,4 +386,297 @@ __global__ void __launch_bounds__(BS)
     buf ^= 1;
   }
 }
+
+
+
+// =============================================================================================
+// Gauss-Seidel / SOR, per-ROW dataflow ("mailbox" sweep) — the default for structurally symmetric
+// matrices.  Same renumbered layout, tasks and ticket scheduling as gs_dataflow_kernel, but the
+// hand-off between dependent rows carries the DATA WITH THE FLAG, the way NCCL's LL protocol does:
+// every relaxed row publishes its new value as one 16-byte store {lo32, epoch, hi32, epoch} into
+// mail[row]; a consumer polls the mailboxes of its earlier-ordered neighbours with 16-byte loads
+// until both epoch words match (8-byte halves are single-copy atomic, so a matching pair of halves
+// IS the value).  No fence, no completion counter, no CTA barrier on the critical path: one hop is
+// store -> L2 -> poll, roughly a third of the counter protocol's fence + count + poll + gather.
+// Rows advance as soon as THEIR neighbours are done; there is no wavefront-wide barrier at all.
+//
+// Throttle: a task of wavefront w first sleeps until some task of wavefront w - 2 has finished
+// (started[] hint), so only ~2 wavefronts' worth of threads ever spin on mailboxes.
+//
+// Anti-dependencies (reading the OLD value of a later-ordered neighbour j) are safe because the
+// pattern is symmetric: j's row contains this row, so j cannot be relaxed before this row publishes,
+// which happens after the old value was read.
+//
+// ctl[0] = ticket, ctl[1] = epoch (gs_mail_prepare_kernel bumps it before every sweep),
+// ctl[(2 + w) * kGsCounterStride] = epoch of the last sweep in which a task of wavefront w finished.
+// =============================================================================================
+__global__ void gs_mail_prepare_kernel(unsigned* ctl) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ctl[0] = 0u;
+    ctl[1] = ctl[1] + 1u;
+  }
+}
+__device__ __forceinline__ void st_mail(uint4* p, double v, unsigned e) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(e),
+               "r"((unsigned)__double2hiint(v)), "r"(e)
+               : "memory");
+}
+// four mailbox polls issued back to back
+__device__ __forceinline__ void ld_mail4(uint4 (&m)[4], const uint4* const (&a)[4]) {
+  asm volatile(
+      "ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%16];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%4, %5, %6, %7}, [%17];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%8, %9, %10, %11}, [%18];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%12, %13, %14, %15}, [%19];"
+      : "=r"(m[0].x), "=r"(m[0].y), "=r"(m[0].z), "=r"(m[0].w), "=r"(m[1].x), "=r"(m[1].y), "=r"(m[1].z), "=r"(m[1].w),
+        "=r"(m[2].x), "=r"(m[2].y), "=r"(m[2].z), "=r"(m[2].w), "=r"(m[3].x), "=r"(m[3].y), "=r"(m[3].z), "=r"(m[3].w)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3])
+      : "memory");
+}
+
+template <int T, int BS>
+__global__ void __launch_bounds__(BS)
+    gs_mail_kernel(int ntasks, const int4* __restrict__ tasks, unsigned* ctl, const int* __restrict__ rowptr,
+                   const int* __restrict__ col, const double* __restrict__ val, double* x, const double* __restrict__ b,
+                   uint4* mail, double omega, int sor, int backward, int opaque_zero, int poll_sleep, int gate_sleep) {
+  __shared__ int s_task[2];
+  const int tid = threadIdx.x, g = tid / T, lane = tid % T;
+  const unsigned e = ld_relaxed_u32(ctl + 1);
+  if (tid == 0) s_task[0] = (int)atomicAdd(&ctl[0], 1u);
+  __syncthreads();
+  int cur = s_task[0], buf = 0;
+  while (cur < ntasks) {
+    if (tid == 0) s_task[buf ^ 1] = (int)atomicAdd(&ctl[0], 1u);   // next ticket, off the critical path
+    const int4 tk = __ldg(tasks + cur);
+    const bool active = g < tk.y;
+    const int row = active ? tk.x + g : -1;
+    int ks = 0, ke = 0;
+    double bv = 0.0, xold = 0.0;
+    if (active) {
+      ks = __ldg(rowptr + row);
+      ke = __ldg(rowptr + row + 1);
+      if (lane == 0) {
+        bv = __ldg(b + row);
+        xold = __ldcg(x + row);   // only this row's own update ever writes x[row] during the sweep
+      }
+    }
+    int c[kGsPrefetch];
+    double v[kGsPrefetch];
+#pragma unroll
+    for (int j = 0; j < kGsPrefetch; ++j) {
+      const int k = ks + lane + j * T;
+      const bool in = k < ke;
+      c[j] = in ? __ldg(col + k) : -1;
+      v[j] = in ? __ldg(val + k) : 0.0;
+    }
+    // later-ordered neighbours keep their old value until this row has published: fetch them now
+    double xn[kGsPrefetch];   // neighbour values: later ones now, earlier ones from the mailboxes below
+    unsigned need = 0u;       // slots still waiting for an earlier-ordered neighbour
+    {
+      const double* a[kGsPrefetch];
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) {
+        const bool valid = c[j] >= 0 && c[j] != row;
+        const bool earlier = valid && (backward ? c[j] > row : c[j] < row);
+        if (earlier) need |= 1u << j;
+        a[j] = (valid && !earlier) ? x + c[j] : &g_gs_zero;
+      }
+      ldcg_burst8(xn, a);
+    }
+    if (tk.z >= 2) {   // throttle: stay asleep until wavefront tk.z - 2 has begun to finish
+      if (tid == 0) {
+        const unsigned* hint = ctl + (size_t)tk.z * kGsCounterStride;   // (2 + (tk.z - 2))
+        while (ld_relaxed_u32(hint) != e) if (gate_sleep) __nanosleep(gate_sleep);
+      }
+      __syncthreads();
+    }
+    // ---- poll the mailboxes of the earlier-ordered neighbours, four slots at a time ----
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      unsigned want = (need >> (4 * half)) & 0xfu;
+      while (want) {
+        const uint4* a[4];
+        uint4 m[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[j] = ((want >> j) & 1u) ? mail + c[4 * half + j] : mail + (row >= 0 ? row : 0);
+        ld_mail4(m, a);
+        {   // pin the four polls in front of the first flag test (see pin_burst8)
+          const unsigned dep = (m[0].y & m[1].y & m[2].y & m[3].y) & (unsigned)opaque_zero;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) m[j].y |= dep;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (((want >> j) & 1u) && m[j].y == e && m[j].w == e) {
+            xn[4 * half + j] = __hiloint2double((int)m[j].z, (int)m[j].x);
+            want &= ~(1u << j);
+          }
+        if (want && poll_sleep) __nanosleep(poll_sleep);
+      }
+    }
+    double rsum = 0.0, d = 0.0;
+#pragma unroll
+    for (int j = 0; j < kGsPrefetch; ++j) {
+      if (c[j] == row && c[j] >= 0) d = v[j];
+      else rsum = __dadd_rn(rsum, __dmul_rn(v[j], xn[j]));   // idle slots add an exact +0
+    }
+    for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {   // rows longer than T * kGsPrefetch
+      const int cc = __ldg(col + k);
+      const double vv = __ldg(val + k);
+      if (cc == row) { d = vv; continue; }
+      double xv;
+      if (backward ? cc > row : cc < row) {
+        uint4 m;
+        do {
+          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(m.x), "=r"(m.y), "=r"(m.z), "=r"(m.w)
+                       : "l"(mail + cc)
+                       : "memory");
+        } while (m.y != e || m.w != e);
+        xv = __hiloint2double((int)m.z, (int)m.x);
+      } else {
+        xv = __ldcg(x + cc);
+      }
+      rsum = __dadd_rn(rsum, __dmul_rn(vv, xv));
+    }
+    if (T > 1) {
+      rsum = lanes_sum<T>(rsum);
+      d = lanes_sum<T>(d);
+    }
+    if (active && lane == 0) {
+      double xnew = xold;
+      if (d != 0.0) {
+        const double r = __dsub_rn(bv, rsum);
+        xnew = sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d);
+      }
+      st_mail(mail + row, xnew, e);   // publish first: this is what dependants spin on
+      __stcg(x + row, xnew);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      volatile unsigned* mine = ctl + (size_t)(2 + tk.z) * kGsCounterStride;
+      *mine = e;   // throttle hint only: no ordering required
+    }
+    cur = s_task[buf ^ 1];
+    buf ^= 1;
+  }
+}
+
+
+// =============================================================================================
+// Gauss-Seidel / SOR on a SMALL level: one CTA (1024 threads) sweeps the whole level.
+// Coarse levels have thousands of tiny wavefronts (20-200 rows each); across SMs every wavefront costs
+// a 0.5-2 us L2 hand-off, inside one SM it costs a bar.sync.  The matrix (renumbered, so wavefronts are
+// contiguous row ranges) is streamed through the same TMA tile pipeline as the SpMV kernels — row
+// pointers, column indices, values and b are in shared memory before they are needed — and x lives in
+// shared memory as well when the level fits (XS), else it is read/written through L2 (ld.cg / st.cg,
+// ordered by the barrier).  T lanes cooperate on a row.
+// lvlptr: forward wavefront boundaries (row indices); a backward sweep walks tiles and wavefronts in reverse.
+// =============================================================================================
+constexpr int kGsCtaThreads = 1024;
+struct __align__(16) GsCtaStage {
+  double val[kTileNnz + 8];
+  double b[kTileRowsMax + 8];
+  int col[kTileNnz + 8];
+  int rp[kTileRowsMax + 8];
+};
+static_assert(sizeof(GsCtaStage) % 16 == 0, "stage must keep 16-byte alignment");
+
+__device__ __forceinline__ void gs_cta_issue(GsCtaStage& S, uint64_t* bar, const int4 m, const int* __restrict__ rowptr,
+                                             const int* __restrict__ col, const double* __restrict__ val,
+                                             const double* __restrict__ b) {
+  const int ka = m.z & ~3, kcnt = (m.w - ka + 3) & ~3;
+  const int ra = m.x & ~3, rcnt = (m.y + 1 - ra + 3) & ~3;
+  mbar_expect_tx(bar, (uint32_t)(kcnt * 12 + rcnt * 4 + rcnt * 8));
+  if (kcnt) {
+    bulk_g2s(S.val, val + ka, (uint32_t)kcnt * 8u, bar);
+    bulk_g2s(S.col, col + ka, (uint32_t)kcnt * 4u, bar);
+  }
+  bulk_g2s(S.rp, rowptr + ra, (uint32_t)rcnt * 4u, bar);
+  bulk_g2s(S.b, b + ra, (uint32_t)rcnt * 8u, bar);
+}
+
+template <int T, bool XS>
+__global__ void __launch_bounds__(kGsCtaThreads, 1)
+    gs_cta_kernel(int n, int ntiles, const int4* __restrict__ meta, const int* __restrict__ rowptr, const int* __restrict__ col,
+                  const double* __restrict__ val, const int* __restrict__ lvlptr, int nlev, double* x, const double* __restrict__ b,
+                  double omega, int sor, int backward) {
+  extern __shared__ __align__(128) unsigned char gs_smem[];
+  GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_smem);
+  double* xs = reinterpret_cast<double*>(gs_smem + kStages * sizeof(GsCtaStage));
+  __shared__ __align__(8) uint64_t full[kStages];
+  const int tid = threadIdx.x;
+  constexpr int G = kGsCtaThreads / T;
+  const int g = tid / T, lane = tid % T;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
+  if (XS)
+    for (int i = tid; i < n; i += kGsCtaThreads) xs[i] = __ldcg(x + i);
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s)
+      if (s < ntiles) gs_cta_issue(st[s], &full[s], __ldg(meta + (backward ? ntiles - 1 - s : s)), rowptr, col, val, b);
+  }
+  int w = backward ? nlev - 1 : 0;   // current wavefront (forward numbering)
+  int s = 0;
+  uint32_t parity = 0;
+  for (int i = 0; i < ntiles; ++i) {
+    const int4 m = __ldg(meta + (backward ? ntiles - 1 - i : i));
+    const int ka = m.z & ~3, ra = m.x & ~3;
+    mbar_wait(&full[s], parity);
+    const GsCtaStage& S = st[s];
+    int r = backward ? m.y : m.x;   // forward: next row to relax; backward: one past it
+    while (backward ? r > m.x : r < m.y) {
+      int a, e;   // segment [a, e): the part of wavefront w inside this tile
+      if (!backward) {
+        while (__ldg(lvlptr + w + 1) <= r) ++w;
+        a = r;
+        e = min(m.y, __ldg(lvlptr + w + 1));
+      } else {
+        while (__ldg(lvlptr + w) >= r) --w;
+        e = r;
+        a = max(m.x, __ldg(lvlptr + w));
+      }
+      for (int base = a; base < e; base += G) {   // uniform trip count: shuffles stay converged
+        const int row = base + g;
+        double rsum = 0.0, d = 0.0;
+        if (row < e) {
+          const int ks = S.rp[row - ra] - ka, ke = S.rp[row - ra + 1] - ka;
+          for (int k = ks + lane; k < ke; k += T) {
+            const int c = S.col[k];
+            const double v = S.val[k];
+            if (c == row) d = v;
+            else rsum = __dadd_rn(rsum, __dmul_rn(v, XS ? xs[c] : __ldcg(x + c)));
+          }
+        }
+        if (T > 1) {
+          rsum = lanes_sum<T>(rsum);
+          d = lanes_sum<T>(d);
+        }
+        if (row < e && lane == 0 && d != 0.0) {
+          const double rr = __dsub_rn(S.b[row - ra], rsum);
+          const double xold = XS ? xs[row] : (sor ? __ldcg(x + row) : 0.0);
+          const double xnew = sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), rr)) : __ddiv_rn(rr, d);
+          if (XS) xs[row] = xnew;
+          else __stcg(x + row, xnew);
+        }
+      }
+      __syncthreads();   // the wavefront (segment) is relaxed: its x is visible to the next one
+      r = backward ? a : e;
+    }
+    // every thread is past the barrier that closed the tile's last segment: refill the stage
+    if (tid == 0 && i + kStages < ntiles)
+      gs_cta_issue(st[s], &full[s], __ldg(meta + (backward ? ntiles - 1 - (i + kStages) : i + kStages)), rowptr, col, val, b);
+    if (++s == kStages) { s = 0; parity ^= 1u; }
+  }
+  if (XS) {
+    __syncthreads();
+    for (int i = tid; i < n; i += kGsCtaThreads) x[i] = xs[i];
+  }
+}
+
 }  // namespace b200amg

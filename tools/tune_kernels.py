@@ -49,7 +49,7 @@ for chunk in [int(c) for c in args.chunks.split(",")]:
             out[names[what]] = {"ms": round(ms, 4), "GBs": round(alg[what] / ms / 1e6, 1)}
         print(json.dumps(out), flush=True)
 if args.smoother == "gs":
-    for mode in (1, 0):
+    for mode in (2, 1):
         dev.set_option(3, mode)
         for lv in range(dev.nlevels - 1):
             info = dev.level_info(lv)
@@ -59,3 +59,24 @@ if args.smoother == "gs":
             print(json.dumps({"gs_mode": mode, "level": lv, "n": n, "nnz": nnz, "wavefronts": info["wavefronts"],
                               "sgs_ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1),
                               "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}), flush=True)
+if args.smoother == "gs" and os.environ.get("SWEEP_SLEEP"):
+    dev.set_option(3, 2)
+    for poll, gate in ((0, 100), (0, 0), (40, 100), (0, 500), (100, 1000)):
+        dev.set_option(5, poll)
+        dev.set_option(6, gate)
+        row = []
+        for lv in range(dev.nlevels - 1):
+            info = dev.level_info(lv)
+            ms = dev.time_kernel(lv, 2, reps=3)
+            row.append(round(1e3 * ms / max(2 * info["wavefronts"], 1), 2))
+        print(json.dumps({"poll_sleep": poll, "gate_sleep": gate, "us_per_wavefront_by_level": row}), flush=True)
+if args.smoother == "gs" and os.environ.get("SWEEP_CTA"):
+    for cta_rows in (65536, 0):
+        dev.set_option(3, 2)
+        dev.set_option(7, cta_rows)
+        row = []
+        for lv in range(dev.nlevels - 1):
+            info = dev.level_info(lv)
+            ms = dev.time_kernel(lv, 2, reps=3)
+            row.append(round(1e3 * ms / max(2 * info["wavefronts"], 1), 2))
+        print(json.dumps({"cta_rows": cta_rows, "us_per_wavefront_by_level": row}), flush=True)
