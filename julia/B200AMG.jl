@@ -1,0 +1,135 @@
+# B200AMG.jl — the reference-side binding of libb200amg.so (include/b200amg.h).
+#
+# NOT RUNNABLE IN THIS IMAGE (no Julia toolchain here or on the GPU box); it is the shim a maintainer of
+# AlgebraicMultigrid.jl would add so that `_solve!`, `ldiv!` and `smooth!` of an existing `MultiLevel`
+# (built by the package's own `ruge_stuben` / `smoothed_aggregation` on the host) run on a B200.
+# The Python mirror in algebraicmultigrid.jl_b200/ calls exactly the same entry points through ctypes
+# and is what the tests and benchmarks of this repository exercise.
+module B200AMG
+
+using AlgebraicMultigrid, SparseArrays, LinearAlgebra
+import AlgebraicMultigrid: MultiLevel, Level, Cycle, V, W, F, Smoother, GaussSeidel, Jacobi, SOR,
+                           ForwardSweep, BackwardSweep, SymmetricSweep, Pinv, QRSolver, Preconditioner
+import LinearAlgebra: ldiv!
+
+const lib = get(ENV, "B200AMG_LIB", "libb200amg")
+
+# ---- b200amg_csc_t / b200amg_smoother_t (include/b200amg.h) -------------------------------------
+struct CscDesc
+    m::Int64; n::Int64
+    colptr::Ptr{Cvoid}; rowval::Ptr{Cvoid}; nzval::Ptr{Float64}
+    index_bits::Int32; index_base::Int32; adjoint::Int32; reserved::Int32
+end
+struct SmootherDesc
+    kind::Int32; sweep::Int32; iter::Int32; reserved::Int32; omega::Float64
+end
+
+# a SparseMatrixCSC{Float64,Int64} (or its lazy Adjoint: RS stores P = R', SA stores R = P') crosses as is
+csc(A::SparseMatrixCSC{Float64,Int64}; adj = false) =
+    CscDesc(size(A, 1), size(A, 2), pointer(A.colptr), pointer(A.rowval), pointer(A.nzval), 64, 1, adj ? 1 : 0, 0)
+csc(A::Adjoint{Float64,<:SparseMatrixCSC{Float64,Int64}}) = csc(parent(A); adj = true)
+
+sweepcode(::ForwardSweep) = Int32(1); sweepcode(::BackwardSweep) = Int32(2); sweepcode(::SymmetricSweep) = Int32(3)
+desc(s::GaussSeidel) = SmootherDesc(1, sweepcode(s.sweep), s.iter, 0, 1.0)
+desc(s::Jacobi)      = SmootherDesc(2, 3, s.iter, 0, s.ω)
+desc(s::SOR)         = SmootherDesc(3, sweepcode(s.sweep), s.iter, 0, s.ω)
+cyclecode(::V) = Int32(0); cyclecode(::W) = Int32(1); cyclecode(::F) = Int32(2)
+
+check(rc) = rc == 0 || error("b200amg error $rc: " * unsafe_string(ccall((:b200amg_last_error, lib), Cstring, ())))
+
+"""Device-resident copy of a `MultiLevel`: upload once, reuse for every solve."""
+mutable struct DeviceMultiLevel
+    handle::Ptr{Cvoid}
+    ml::MultiLevel
+    n::Int
+end
+
+function DeviceMultiLevel(ml::MultiLevel, pre::Smoother = GaussSeidel(), post::Smoother = GaussSeidel();
+                          device::Integer = 0, symmetry::Integer = 0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:b200amg_create, lib), Int32, (Ref{Ptr{Cvoid}}, Int32), h, device))
+    GC.@preserve ml begin
+        for l in ml.levels      # push!(levels, Level(A, P, R, pre, post))  classical.jl:48-52, aggregation.jl:147-151
+            a, p, r = Ref(csc(l.A)), Ref(csc(l.P)), Ref(csc(l.R))
+            check(ccall((:b200amg_add_level, lib), Int32,
+                        (Ptr{Cvoid}, Ref{CscDesc}, Ref{CscDesc}, Ref{CscDesc}, Ref{SmootherDesc}, Ref{SmootherDesc}, Int32),
+                        h[], a, p, r, Ref(desc(pre)), Ref(desc(post)), symmetry))
+        end
+        n = size(ml.final_A, 1)
+        Minv = Matrix(pinv(Matrix(ml.final_A)))      # Pinv (coarse_solver.jl:9-16); inv(A) for the QR/LU solvers
+        check(ccall((:b200amg_set_coarse, lib), Int32, (Ptr{Cvoid}, Ref{CscDesc}, Int64, Ptr{Float64}),
+                    h[], Ref(csc(ml.final_A)), n, Minv))
+    end
+    check(ccall((:b200amg_finalize, lib), Int32, (Ptr{Cvoid},), h[]))
+    d = DeviceMultiLevel(h[], ml, isempty(ml.levels) ? size(ml.final_A, 1) : size(ml.levels[1].A, 1))
+    finalizer(x -> ccall((:b200amg_destroy, lib), Int32, (Ptr{Cvoid},), x.handle), d)
+    return d
+end
+
+"""`_solve!(x, ml, b, cycle; ...)` (src/multilevel.jl:158-198) on the device."""
+function AlgebraicMultigrid._solve!(x::Vector{Float64}, d::DeviceMultiLevel, b::Vector{Float64}, cycle::Cycle = V();
+                                    maxiter::Int = 100, abstol::Real = zero(Float64), reltol::Real = sqrt(eps(Float64)),
+                                    verbose::Bool = false, log::Bool = false, calculate_residual = true, kwargs...)
+    residuals = Vector{Float64}(undef, maxiter + 2)
+    nres, iters = Ref{Int32}(0), Ref{Int32}(0)
+    check(ccall((:b200amg_solve, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Float64, Int32, Ptr{Float64}, Int32,
+                 Ref{Int32}, Ref{Int32}, Int32),
+                d.handle, x, b, cyclecode(cycle), maxiter, abstol, reltol, calculate_residual ? 1 : 0, residuals,
+                length(residuals), nres, iters, 0))
+    resize!(residuals, nres[])
+    if verbose && calculate_residual          # the reference prints the PREVIOUS residual (multilevel.jl:185-187)
+        for itr in 1:iters[]
+            AlgebraicMultigrid.Printf.@printf "Norm of residual at iteration %6d is %.4e\n" itr residuals[itr]
+        end
+    end
+    return log ? (x, residuals) : x
+end
+AlgebraicMultigrid._solve(d::DeviceMultiLevel, b::Vector{Float64}, args...; kwargs...) =
+    AlgebraicMultigrid._solve!(zeros(Float64, size(b)), d, b, args...; kwargs...)
+
+"""`ldiv!(x, p, b)` (src/preconditioner.jl:12-19): x .= 0 (or b), one cycle, no residual."""
+struct DevicePreconditioner{C<:Cycle}
+    d::DeviceMultiLevel
+    init::Symbol
+    cycle::C
+end
+AlgebraicMultigrid.aspreconditioner(d::DeviceMultiLevel, cycle::Cycle = V()) = DevicePreconditioner(d, :zero, cycle)
+function ldiv!(x::Vector{Float64}, p::DevicePreconditioner, b::Vector{Float64})
+    check(ccall((:b200amg_precond, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Int32),
+                p.d.handle, x, b, cyclecode(p.cycle), p.init == :zero ? 1 : 0, 0))
+    return x
+end
+ldiv!(p::DevicePreconditioner, b) = copyto!(b, ldiv!(similar(b), p, b))
+Base.:\(p::DevicePreconditioner, b) = ldiv!(similar(b), p, b)
+
+"""Device-resident preconditioned CG (what the reference's tests get from IterativeSolvers.cg(A, b; Pl = p))."""
+function cg(p::DevicePreconditioner, b::Vector{Float64}; abstol = 0.0, reltol = sqrt(eps(Float64)), maxiter = length(b))
+    x = zeros(length(b)); res = Vector{Float64}(undef, maxiter + 2); nres, iters = Ref{Int32}(0), Ref{Int32}(0)
+    check(ccall((:b200amg_pcg, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Float64, Ptr{Float64}, Int32, Ref{Int32}, Ref{Int32}, Int32),
+                p.d.handle, x, b, cyclecode(p.cycle), maxiter, abstol, reltol, res, length(res), nres, iters, 0))
+    return x
+end
+
+"""`setup_smoother(config, A, symmetry)` / `smooth!(x, s, b)` (src/smoother.jl:1-49) as a device object."""
+mutable struct DeviceSmoother
+    handle::Ptr{Cvoid}
+end
+function AlgebraicMultigrid.setup_smoother(config::Smoother, A::SparseMatrixCSC{Float64,Int64}, symmetry, ::Val{:b200})
+    s = Ref{Ptr{Cvoid}}(C_NULL)
+    sym = symmetry isa AlgebraicMultigrid.NoSymmetry ? 1 : 0
+    rc = GC.@preserve A ccall((:b200amg_smoother_create, lib), Int32, (Ref{Ptr{Cvoid}}, Int32, Ref{CscDesc}, Ref{SmootherDesc}, Int32),
+                              s, 0, Ref(csc(A)), Ref(desc(config)), sym)
+    rc == -3 && throw(SingularException(0))      # DiagonalIndices, smoother.jl:239-241
+    check(rc)
+    d = DeviceSmoother(s[])
+    finalizer(x -> ccall((:b200amg_smoother_destroy, lib), Int32, (Ptr{Cvoid},), x.handle), d)
+    return d
+end
+function AlgebraicMultigrid.smooth!(x::Vector{Float64}, s::DeviceSmoother, b::Vector{Float64})
+    check(ccall((:b200amg_smoother_apply, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int32), s.handle, x, b, 0))
+    return nothing
+end
+
+end # module
