@@ -334,12 +334,15 @@ struct DevCsr {
   void plan_tiles(const HostCsr& h, double mean) {
     ntiles = 0;
     if (nrows == 0 || env_int("B200AMG_NO_STREAM", 0)) return;
+    // lanes per row.  Measured (tools/tune_kernels.py, 256^3 RS hierarchy): stencil rows (<= 8 entries) are
+    // fastest with one thread per row and a single gather burst; for 19-110 entries per row FEWER lanes with the
+    // unrolled loop beat more lanes with bursts (4070 vs 3830 GB/s at 19 entries per row).
     stream_lanes = 1;
     while (stream_lanes < 32 && mean > 12.0 * stream_lanes) stream_lanes *= 2;
     stream_lanes = env_int("B200AMG_STREAM_LANES", stream_lanes);
     const int G = kStreamThreads / stream_lanes;
     int passes = (int)(kTileNnz / std::max(1.0, G * std::max(mean, 1.0)));
-    passes = std::min(std::max(passes, 1), 4);
+    passes = std::min(std::max(passes, 1), 2);   // the kernel prefetches the epilogue operands of two passes
     const int rows_per_tile = std::min(G * passes, kTileRowsMax);
     std::vector<int4> m;
     m.reserve((size_t)(nnz / kTileNnz + nrows / rows_per_tile + 2));

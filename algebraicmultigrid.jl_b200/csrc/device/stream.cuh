@@ -29,6 +29,7 @@ constexpr int kStreamThreads = 256;
 constexpr int kTileNnz = 2048;
 constexpr int kTileRowsMax = 1024;
 constexpr int kStages = 3;
+constexpr int kStreamBurst = 8;   // x gathers a lane issues back to back for a short row
 
 struct __align__(16) StreamStage {
   double val[kTileNnz + 8];
@@ -129,14 +130,16 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
     const int4 m = __ldg(meta + t);
     const int nrows = m.y - m.x, ka = m.z & ~3, rofs = m.x - (m.x & ~3);
     // operands of the epilogue of the first pass: requested before the barrier wait
-    double pre_b = 0.0, pre_x = 0.0, pre_d = 0.0;
-    if (lane == 0 && g < nrows) {
-      const int row = m.x + g;
-      if (MODE == 1 || MODE == 3 || MODE == 4) pre_b = __ldg(b + row);
-      if (MODE == 2) pre_x = y[row];
-      if (MODE == 3 || MODE == 4) pre_x = __ldg(x + row);
-      if (MODE == 4) pre_d = __ldg(diagvals + row);
-    }
+    double pre_b[2] = {0.0, 0.0}, pre_x[2] = {0.0, 0.0}, pre_d[2] = {0.0, 0.0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+      if (lane == 0 && g + q * G < nrows) {
+        const int row = m.x + g + q * G;
+        if (MODE == 1 || MODE == 3 || MODE == 4) pre_b[q] = __ldg(b + row);
+        if (MODE == 2) pre_x[q] = y[row];
+        if (MODE == 3 || MODE == 4) pre_x[q] = __ldg(x + row);
+        if (MODE == 4) pre_d[q] = __ldg(diagvals + row);
+      }
     mbar_wait(&full[s], parity);
     const StreamStage& S = st[s];
     for (int rbase = 0; rbase < nrows; rbase += G) {
@@ -145,15 +148,38 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
       if (r < nrows) {
         const int ks = S.rp[rofs + r] - ka, ke = S.rp[rofs + r + 1] - ka;
         const int row = m.x + r;
+        if (ke - ks <= kStreamBurst * T) {
+          // short row (every stencil row): ALL its x gathers leave in one burst, so the row costs one L2
+          // round trip; the products are then added in the reference's order (idle slots add an exact +0,
+          // as the reference itself does for the diagonal in smooth!: `rsum += ifelse(row == i, z, ...)`)
+          int c[kStreamBurst];
+          double v[kStreamBurst], xv[kStreamBurst];
+#pragma unroll
+          for (int j = 0; j < kStreamBurst; ++j) {
+            const int k = ks + lane + j * T;
+            const bool in = k < ke;
+            c[j] = in ? S.col[k] : -1;
+            v[j] = in ? S.val[k] : 0.0;
+          }
+#pragma unroll
+          for (int j = 0; j < kStreamBurst; ++j) {
+            const bool use = c[j] >= 0 && !(MODE == 3 && c[j] == row);
+            xv[j] = use ? __ldg(x + c[j]) : 0.0;
+            if (MODE == 3 && c[j] == row) diag = v[j];
+          }
+#pragma unroll
+          for (int j = 0; j < kStreamBurst; ++j) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
+        } else {
 #pragma unroll 4
-        for (int k = ks + lane; k < ke; k += T) {
-          const int c = S.col[k];
-          const double v = S.val[k];
-          if (MODE == 3) {
-            if (c == row) diag = v;
-            else sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
-          } else {
-            sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+          for (int k = ks + lane; k < ke; k += T) {
+            const int c = S.col[k];
+            const double v = S.val[k];
+            if (MODE == 3) {
+              if (c == row) diag = v;
+              else sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+            } else {
+              sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));
+            }
           }
         }
       }
@@ -163,8 +189,11 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
       }
       if (lane == 0 && r < nrows) {
         const int row = m.x + r;
-        double bv = pre_b, xv = pre_x, dv = pre_d;
-        if (rbase != 0) {
+        double bv, xv, dv;
+        if (rbase == 0) { bv = pre_b[0]; xv = pre_x[0]; dv = pre_d[0]; }
+        else if (rbase == G) { bv = pre_b[1]; xv = pre_x[1]; dv = pre_d[1]; }
+        else {
+          bv = xv = dv = 0.0;
           if (MODE == 1 || MODE == 3 || MODE == 4) bv = __ldg(b + row);
           if (MODE == 2) xv = y[row];
           if (MODE == 3 || MODE == 4) xv = __ldg(x + row);
