@@ -475,6 +475,10 @@ struct SmootherMatrix {
   HostPerm perm;            // identity unless a sweep smoother renumbered the level
   int *d_new_of_old = nullptr, *d_old_of_new = nullptr;
   // mailbox sweep (stream.cuh: gs_mail_kernel): only for structurally symmetric patterns
+  // wavefront-aligned tile plan of the walked matrix (stream.cuh: gs_tile_kernel)
+  int4* gs_meta = nullptr;
+  int* gs_tile_wave = nullptr;
+  int gs_ntiles = 0, gs_lanes = 1;
   int* d_fwd_lvlptr = nullptr;   // forward wavefront boundaries (single-CTA sweep)
   int nlev = 0;
   bool pattern_symmetric = false;
@@ -542,6 +546,31 @@ struct SmootherMatrix {
       nlev = (int)lvlptr.size() - 1;
     }
     if ((need_fwd || need_bwd) && pattern_symmetric && n > 0) {
+      gs_lanes = 1;
+      while (gs_lanes < 32 && kGsPrefetch * gs_lanes < (mean <= kGsPrefetch ? mean : 1.25 * mean)) gs_lanes *= 2;
+      gs_lanes = env_int("B200AMG_GS_LANES", gs_lanes);
+      const int G = kGsTileThreads / gs_lanes;
+      const int rows_per_tile = G * std::min(std::max(env_int("B200AMG_GS_TILE_PASSES", 1), 1), 4);
+      std::vector<int4> tm;
+      std::vector<int> tw;
+      bool ok = true;
+      for (int wv = 0; wv + 1 < (int)lvlptr.size() && ok; ++wv) {
+        int r = lvlptr[wv];
+        while (r < lvlptr[wv + 1]) {
+          int e2 = r;
+          const int k0 = w.ptr[r];
+          while (e2 < lvlptr[wv + 1] && e2 - r < rows_per_tile && w.ptr[e2 + 1] - k0 <= kTileNnz) ++e2;
+          if (e2 == r) { ok = false; break; }   // a row longer than a tile: the other sweeps take over
+          tm.push_back(make_int4(r, e2, k0, w.ptr[e2]));
+          tw.push_back(wv);
+          r = e2;
+        }
+      }
+      if (ok) {
+        gs_meta = dev_upload(tm);
+        gs_tile_wave = dev_upload(tw);
+        gs_ntiles = (int)tm.size();
+      }
       mail = dev_alloc<uint4>(n + 8);
       CUDA_OK(cudaMemset(mail, 0, sizeof(uint4) * (size_t)(n + 8)));
       const int64_t words = (int64_t)(lvlptr.size() + 4) * kGsCounterStride;
@@ -551,8 +580,8 @@ struct SmootherMatrix {
   }
   void release() {
     A.release(); At.release(); fwd.release(); bwd.release();
-    cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr);
-    d_fwd_lvlptr = nullptr;
+    cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr); cudaFree(gs_meta); cudaFree(gs_tile_wave);
+    d_fwd_lvlptr = nullptr; gs_meta = nullptr; gs_tile_wave = nullptr; gs_ntiles = 0;
     diag = nullptr; d_new_of_old = d_old_of_new = nullptr; mail = nullptr; mail_ctl = nullptr;
   }
 };
@@ -632,6 +661,7 @@ struct b200amg_hierarchy {
   bool use_graphs = true;
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
+  int gs_tile_any_lanes = 0;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
@@ -831,6 +861,39 @@ static void launch_mail(H* h, const SmootherMatrix& M, const DevCsr& A, const De
   }
 #undef B200AMG_ML_CASE
 }
+template <int T>
+static int gs_tile_ctas() {
+  static int cached = 0;
+  if (!cached) {
+    CUDA_OK(cudaFuncSetAttribute(gs_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * sizeof(GsCtaStage))));
+    int per_sm = 0;
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_tile_kernel<T>, kGsTileThreads, kStages * sizeof(GsCtaStage)));
+    cached = std::max(1, per_sm) * kNumSM;
+  }
+  return cached;
+}
+template <int T>
+static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                             int sor) {
+  const int ctas = std::min(M.gs_ntiles, gs_tile_ctas<T>());
+  gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(M.mail_ctl);
+  count_launch(h);
+  gs_tile_kernel<T><<<ctas, kGsTileThreads, kStages * sizeof(GsCtaStage), h->stream>>>(
+      M.gs_ntiles, M.gs_meta, M.gs_tile_wave, M.nlev, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor, sc.backward, h->opaque_zero,
+      h->gs_poll_sleep, h->gs_gate_sleep);
+  count_launch(h);
+}
+static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                           int sor) {
+  switch (M.gs_lanes) {
+    case 1: launch_gs_tile_T<1>(h, M, A, sc, x, b, w, sor); break;
+    case 2: launch_gs_tile_T<2>(h, M, A, sc, x, b, w, sor); break;
+    case 4: launch_gs_tile_T<4>(h, M, A, sc, x, b, w, sor); break;
+    case 8: launch_gs_tile_T<8>(h, M, A, sc, x, b, w, sor); break;
+    case 16: launch_gs_tile_T<16>(h, M, A, sc, x, b, w, sor); break;
+    default: launch_gs_tile_T<32>(h, M, A, sc, x, b, w, sor); break;
+  }
+}
 constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
 template <int T, bool XS>
 static void gs_cta_set_attr() {
@@ -877,7 +940,10 @@ static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, d
   // wavefront-counter sweep in between.
   if (h->gs_mode >= 1 && M.n <= h->gs_cta_rows && A.ntiles > 0 && M.d_fwd_lvlptr) { launch_gs_cta(h, M, A, sc, x, b, w, sor); return; }
   const bool wide = sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width;
-  if (h->gs_mode == 2 && M.mail && wide) { launch_mail(h, M, A, sc, x, b, w, sor); return; }
+  // measured, 256^3 RS hierarchy (us per wavefront): TMA-fed mailbox sweep 2.3 at one thread per row (stencil rows)
+  // but 6-7 with several lanes per row, where the ticket mailbox sweep does 3.0-4.7 and the counter sweep 4.6-6.0
+  if (h->gs_mode == 2 && M.mail && M.gs_ntiles > 0 && wide && (M.gs_lanes == 1 || h->gs_tile_any_lanes)) { launch_gs_tile(h, M, A, sc, x, b, w, sor); return; }
+  if (h->gs_mode >= 2 && M.mail && wide) { launch_mail(h, M, A, sc, x, b, w, sor); return; }
   if (h->gs_mode >= 1) { launch_dataflow(h, A, sc, x, b, w, sor); return; }
   switch (A.lanes) {
     case 2: launch_sweep_T<2>(h, A, sc, x, b, w, sor); break;
@@ -1325,11 +1391,13 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   stream_kernels_init();
   gs_cta_kernels_init();
+  gs_tile_ctas<1>(); gs_tile_ctas<2>(); gs_tile_ctas<4>(); gs_tile_ctas<8>(); gs_tile_ctas<16>(); gs_tile_ctas<32>();
   h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
   h->gs_mode = env_int("B200AMG_GS_MODE", 2);
   h->gs_acquire = env_int("B200AMG_GS_ACQUIRE", 0);
   h->gs_cta_rows = env_int("B200AMG_GS_CTA_ROWS", 12288);
   h->gs_mail_min_width = env_int("B200AMG_GS_MAIL_MIN_WIDTH", 1024);
+  h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 0);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);

@@ -708,4 +708,198 @@ __global__ void __launch_bounds__(kGsCtaThreads, 1)
   }
 }
 
+
+// =============================================================================================
+// Gauss-Seidel / SOR on LARGE levels: the mailbox protocol (gs_mail_kernel) fed by the TMA tile ring.
+// Persistent CTAs own every gridDim-th tile of a wavefront-ALIGNED tile plan (a tile never crosses a
+// wavefront boundary, so rows of a tile are mutually independent); tile data — row pointers, column
+// indices, values, b — arrives in shared memory through a 3-stage bulk-copy ring, so between two
+// tiles a CTA pays no ticket atomic and no dependent load chain.  Per row: later-ordered neighbours
+// are read from x (old values), earlier-ordered ones are polled from their 16-byte mailboxes in ONE
+// burst, the row is relaxed in the reference's accumulation order and published.
+// Deadlock freedom: tiles are claimed by ticket in sweep order (three ahead, to keep the ring full), so
+// a tile is only ever held by a resident CTA that walks its claims in order, and the lowest unfinished
+// tile depends only on finished ones — for any grid size.
+// =============================================================================================
+constexpr int kGsTileThreads = 256;
+
+// eight mailbox polls issued back to back
+__device__ __forceinline__ void ld_mail8(uint4 (&m)[8], const uint4* const (&a)[8]) {
+  asm volatile(
+      "ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%4, %5, %6, %7}, [%33];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%8, %9, %10, %11}, [%34];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%12, %13, %14, %15}, [%35];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%16, %17, %18, %19}, [%36];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%20, %21, %22, %23}, [%37];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%24, %25, %26, %27}, [%38];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%28, %29, %30, %31}, [%39];"
+      : "=r"(m[0].x), "=r"(m[0].y), "=r"(m[0].z), "=r"(m[0].w), "=r"(m[1].x), "=r"(m[1].y), "=r"(m[1].z), "=r"(m[1].w),
+        "=r"(m[2].x), "=r"(m[2].y), "=r"(m[2].z), "=r"(m[2].w), "=r"(m[3].x), "=r"(m[3].y), "=r"(m[3].z), "=r"(m[3].w),
+        "=r"(m[4].x), "=r"(m[4].y), "=r"(m[4].z), "=r"(m[4].w), "=r"(m[5].x), "=r"(m[5].y), "=r"(m[5].z), "=r"(m[5].w),
+        "=r"(m[6].x), "=r"(m[6].y), "=r"(m[6].z), "=r"(m[6].w), "=r"(m[7].x), "=r"(m[7].y), "=r"(m[7].z), "=r"(m[7].w)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
+      : "memory");
+}
+template <int T>
+__device__ __forceinline__ double group_lanes_sum(double v, unsigned mask) {
+#pragma unroll
+  for (int o = T / 2; o > 0; o >>= 1) v += __shfl_down_sync(mask, v, o, T);
+  return v;
+}
+
+// meta[t] = {first row, end row, first nnz, end nnz}; tile_wave[t] = wavefront (forward numbering)
+template <int T>
+__global__ void __launch_bounds__(kGsTileThreads, 2)
+    gs_tile_kernel(int ntiles, const int4* __restrict__ meta, const int* __restrict__ tile_wave, int nlev, unsigned* ctl,
+                   const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, double* x,
+                   const double* __restrict__ b, uint4* mail, double omega, int sor, int backward, int opaque_zero,
+                   int poll_sleep, int gate_sleep) {
+  extern __shared__ __align__(128) unsigned char gs_tile_smem[];
+  GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_tile_smem);
+  __shared__ __align__(8) uint64_t full[kStages];
+  const int tid = threadIdx.x, g = tid / T, lane = tid % T;
+  __shared__ int s_tile[kStages];   // tiles claimed (by ticket, in sweep order) for the stages of the ring
+  const unsigned e = ld_relaxed_u32(ctl + 1);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      const int t = (int)atomicAdd(&ctl[0], 1u);
+      s_tile[s] = t;
+      if (t < ntiles) gs_cta_issue(st[s], &full[s], __ldg(meta + (backward ? ntiles - 1 - t : t)), rowptr, col, val, b);
+    }
+  }
+  __syncthreads();
+  int s = 0;
+  uint32_t parity = 0;
+  for (;;) {
+    const int t = s_tile[s];
+    if (t >= ntiles) break;   // tickets are handed out in order: the first invalid one ends this CTA's work
+    int tnext = 0;
+    if (tid == 0) tnext = (int)atomicAdd(&ctl[0], 1u);   // the ticket that will refill this stage, requested early
+    const int tile = backward ? ntiles - 1 - t : t;
+    const int4 m = __ldg(meta + tile);
+    const int wf = __ldg(tile_wave + tile);
+    const int w = backward ? nlev - 1 - wf : wf;   // wavefront in sweep order
+    const int ka = m.z & ~3, ra = m.x & ~3;
+    constexpr int G = kGsTileThreads / T;   // rows relaxed per pass
+    const int nrows = m.y - m.x;
+    const double xold0 = (g < nrows && lane == 0) ? __ldcg(x + m.x + g) : 0.0;   // first pass: requested before the waits
+    mbar_wait(&full[s], parity);
+    const GsCtaStage& S = st[s];
+    for (int rbase = 0; rbase < nrows; rbase += G) {   // rows of a tile are mutually independent
+      const bool active = rbase + g < nrows;
+      const int row = active ? m.x + rbase + g : -1;
+      const double xold = rbase == 0 ? xold0 : ((active && lane == 0) ? __ldcg(x + row) : 0.0);
+      int ks = 0, ke = 0;
+      if (active) {
+        ks = S.rp[row - ra] - ka;
+        ke = S.rp[row - ra + 1] - ka;
+      }
+      int c[kGsPrefetch];
+      double v[kGsPrefetch];
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) {
+        const int k = ks + lane + j * T;
+        const bool in = k < ke;
+        c[j] = in ? S.col[k] : -1;
+        v[j] = in ? S.val[k] : 0.0;
+      }
+      double xn[kGsPrefetch];
+      unsigned need = 0u;
+      {
+        const double* a[kGsPrefetch];
+#pragma unroll
+        for (int j = 0; j < kGsPrefetch; ++j) {
+          const bool valid = c[j] >= 0 && c[j] != row;
+          const bool earlier = valid && (backward ? c[j] > row : c[j] < row);
+          if (earlier) need |= 1u << j;
+          a[j] = (valid && !earlier) ? x + c[j] : &g_gs_zero;
+        }
+        ldcg_burst8(xn, a);   // old values of later-ordered neighbours: in flight while we wait / poll below
+      }
+      if (rbase == 0 && w >= 2) {   // throttle: stay off the mailboxes until wavefront w - 2 has begun to finish
+        if (tid == 0) {
+          const unsigned* hint = ctl + (size_t)w * kGsCounterStride;   // (2 + (w - 2))
+          while (ld_relaxed_u32(hint) != e)
+            if (gate_sleep) __nanosleep(gate_sleep);
+        }
+        __syncthreads();
+      }
+      while (need) {
+        const uint4* a[kGsPrefetch];
+        uint4 mm[kGsPrefetch];
+#pragma unroll
+        for (int j = 0; j < kGsPrefetch; ++j) a[j] = ((need >> j) & 1u) ? mail + c[j] : mail + (row >= 0 ? row : 0);
+        ld_mail8(mm, a);
+        {
+          unsigned dep = mm[0].y;
+#pragma unroll
+          for (int j = 1; j < kGsPrefetch; ++j) dep &= mm[j].y;
+          dep &= (unsigned)opaque_zero;
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j) mm[j].y |= dep;
+        }
+#pragma unroll
+        for (int j = 0; j < kGsPrefetch; ++j)
+          if (((need >> j) & 1u) && mm[j].y == e && mm[j].w == e) {
+            xn[j] = __hiloint2double((int)mm[j].z, (int)mm[j].x);
+            need &= ~(1u << j);
+          }
+        if (need && poll_sleep) __nanosleep(poll_sleep);
+      }
+      double rsum = 0.0, d = 0.0;
+#pragma unroll
+      for (int j = 0; j < kGsPrefetch; ++j) {
+        if (c[j] == row && c[j] >= 0) d = v[j];
+        else rsum = __dadd_rn(rsum, __dmul_rn(v[j], xn[j]));
+      }
+      for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {   // rows longer than T * kGsPrefetch
+        const int cc = S.col[k];
+        const double vv = S.val[k];
+        if (cc == row) { d = vv; continue; }
+        double xv;
+        if (backward ? cc > row : cc < row) {
+          uint4 q;
+          do {
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                         : "l"(mail + cc)
+                         : "memory");
+          } while (q.y != e || q.w != e);
+          xv = __hiloint2double((int)q.z, (int)q.x);
+        } else {
+          xv = __ldcg(x + cc);
+        }
+        rsum = __dadd_rn(rsum, __dmul_rn(vv, xv));
+      }
+      if (T > 1) {
+        const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << ((tid & 31) / T * T));
+        rsum = group_lanes_sum<T>(rsum, gmask);
+        d = group_lanes_sum<T>(d, gmask);
+      }
+      if (active && lane == 0) {
+        double xnew = xold;
+        if (d != 0.0) {
+          const double r = __dsub_rn(S.b[row - ra], rsum);
+          xnew = sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d);
+        }
+        st_mail(mail + row, xnew, e);
+        __stcg(x + row, xnew);
+      }
+    }
+    __syncthreads();   // stage s is free; the tile is published
+    if (tid == 0) {
+      volatile unsigned* mine = ctl + (size_t)(2 + w) * kGsCounterStride;
+      *mine = e;   // throttle hint only
+      s_tile[s] = tnext;   // read again kStages tiles (>= kStages barriers) from now
+      if (tnext < ntiles) gs_cta_issue(st[s], &full[s], __ldg(meta + (backward ? ntiles - 1 - tnext : tnext)), rowptr, col, val, b);
+    }
+    if (++s == kStages) { s = 0; parity ^= 1u; }
+  }
+}
+
 }  // namespace b200amg

@@ -49,7 +49,7 @@ for chunk in [int(c) for c in args.chunks.split(",")]:
             out[names[what]] = {"ms": round(ms, 4), "GBs": round(alg[what] / ms / 1e6, 1)}
         print(json.dumps(out), flush=True)
 if args.smoother == "gs":
-    for mode in (2, 1):
+    for mode in (2, 3, 1):
         dev.set_option(3, mode)
         for lv in range(dev.nlevels - 1):
             info = dev.level_info(lv)
