@@ -659,6 +659,7 @@ struct b200amg_hierarchy {
   int64_t cycle_graph_launches[3] = {0, 0, 0};
   cudaGraphExec_t resnorm_graph = nullptr;
   bool use_graphs = true;
+  bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
   int gs_tile_any_lanes = 0;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
@@ -1205,17 +1206,45 @@ static void cycle_body_part(H* h, int cycle) {
   NCCL_OK(nc.GroupEnd());
   h->collectives++;
   if (pl.rank == 0) {
-    CUDA_OK(cudaMemsetAsync(L0.coarse_x, 0, sizeof(double) * (size_t)std::max<int64_t>(L0.nc, 1), h->stream));   // :226
-    if (h->levels.size() == 1) {
-      coarse_solve(h, L0.coarse_x, L0.coarse_b);                                  // :228
-    } else if (cycle == B200AMG_CYCLE_V) {
-      solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, true);
-    } else if (cycle == B200AMG_CYCLE_W) {
-      solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, true);
-      solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, false);
+    // everything below the partitioned level is a static kernel sequence on this rank: one graph per cycle type
+    auto coarse_part = [&]() {
+      CUDA_OK(cudaMemsetAsync(L0.coarse_x, 0, sizeof(double) * (size_t)std::max<int64_t>(L0.nc, 1), h->stream));   // :226
+      if (h->levels.size() == 1) {
+        coarse_solve(h, L0.coarse_x, L0.coarse_b);                                  // :228
+      } else if (cycle == B200AMG_CYCLE_V) {
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, true);
+      } else if (cycle == B200AMG_CYCLE_W) {
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, true);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, false);
+      } else {
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_F, L0.coarse_b, 1, true);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, false);
+      }
+    };
+    if (h->part_graphs && !h->cycle_graph[cycle] && h->cycle_graph_launches[cycle] >= 0 && !h->profiling) {
+      cudaGraph_t gr = nullptr;
+      h->capturing = true;
+      h->capture_count = 0;
+      CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+      try {
+        coarse_part();
+      } catch (...) {
+        cudaStreamEndCapture(h->stream, &gr);
+        if (gr) cudaGraphDestroy(gr);
+        h->capturing = false;
+        throw;
+      }
+      CUDA_OK(cudaStreamEndCapture(h->stream, &gr));
+      h->capturing = false;
+      CUDA_OK(cudaGraphInstantiate(&h->cycle_graph[cycle], gr, 0));
+      CUDA_OK(cudaGraphDestroy(gr));
+      h->cycle_graph_launches[cycle] = h->capture_count;
+    }
+    if (h->part_graphs && h->cycle_graph[cycle]) {
+      CUDA_OK(cudaGraphLaunch(h->cycle_graph[cycle], h->stream));
+      h->launches += h->cycle_graph_launches[cycle];
     } else {
-      solve_level(h, L0.coarse_x, B200AMG_CYCLE_F, L0.coarse_b, 1, true);
-      solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, false);
+      coarse_part();
     }
   }
   NCCL_OK(nc.GroupStart());                                                      // coarse_x windows <- rank 0
