@@ -662,7 +662,7 @@ struct b200amg_hierarchy {
   bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
-  int gs_tile_any_lanes = 0;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
+  int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
@@ -914,10 +914,10 @@ static void launch_gs_cta_T(H* h, const SmootherMatrix& M, const DevCsr& A, cons
   const size_t smem = kStages * sizeof(GsCtaStage) + (xs ? (size_t)M.n * sizeof(double) : 0);
   if (xs)
     gs_cta_kernel<T, true><<<1, kGsCtaThreads, smem, h->stream>>>((int)M.n, A.ntiles, A.meta, A.ptr, A.idx, A.val, M.d_fwd_lvlptr, M.nlev,
-                                                                 x, b, w, sor, sc.backward);
+                                                                 x, b, w, sor, sc.backward, h->opaque_zero);
   else
     gs_cta_kernel<T, false><<<1, kGsCtaThreads, smem, h->stream>>>((int)M.n, A.ntiles, A.meta, A.ptr, A.idx, A.val, M.d_fwd_lvlptr,
-                                                                  M.nlev, x, b, w, sor, sc.backward);
+                                                                  M.nlev, x, b, w, sor, sc.backward, h->opaque_zero);
   count_launch(h);
 }
 static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
@@ -1426,7 +1426,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_acquire = env_int("B200AMG_GS_ACQUIRE", 0);
   h->gs_cta_rows = env_int("B200AMG_GS_CTA_ROWS", 12288);
   h->gs_mail_min_width = env_int("B200AMG_GS_MAIL_MIN_WIDTH", 1024);
-  h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 0);
+  h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 1);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
@@ -2113,6 +2113,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_ACQUIRE: h->gs_acquire = (int)value; break;
     case B200AMG_OPT_GS_POLL_SLEEP: h->gs_poll_sleep = (int)value; break;
     case B200AMG_OPT_GS_CTA_ROWS: h->gs_cta_rows = (int64_t)value; break;
+    case B200AMG_OPT_GS_MAIL_MIN_WIDTH: h->gs_mail_min_width = (int64_t)value; break;
     case B200AMG_OPT_GS_GATE_SLEEP: h->gs_gate_sleep = (int)value; break;
     default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown option %d", option);
   }

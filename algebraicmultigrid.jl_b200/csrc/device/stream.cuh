@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(BS)
           }
         if (want && poll_sleep) __nanosleep(poll_sleep);
       }
+      __syncwarp();   // lanes leave the poll loop at different times: reconverge before going on
     }
     double rsum = 0.0, d = 0.0;
 #pragma unroll
@@ -629,7 +630,7 @@ template <int T, bool XS>
 __global__ void __launch_bounds__(kGsCtaThreads, 1)
     gs_cta_kernel(int n, int ntiles, const int4* __restrict__ meta, const int* __restrict__ rowptr, const int* __restrict__ col,
                   const double* __restrict__ val, const int* __restrict__ lvlptr, int nlev, double* x, const double* __restrict__ b,
-                  double omega, int sor, int backward) {
+                  double omega, int sor, int backward, int opaque_zero) {
   extern __shared__ __align__(128) unsigned char gs_smem[];
   GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_smem);
   double* xs = reinterpret_cast<double*>(gs_smem + kStages * sizeof(GsCtaStage));
@@ -673,13 +674,46 @@ __global__ void __launch_bounds__(kGsCtaThreads, 1)
       for (int base = a; base < e; base += G) {   // uniform trip count: shuffles stay converged
         const int row = base + g;
         double rsum = 0.0, d = 0.0;
-        if (row < e) {
-          const int ks = S.rp[row - ra] - ka, ke = S.rp[row - ra + 1] - ka;
-          for (int k = ks + lane; k < ke; k += T) {
-            const int c = S.col[k];
-            const double v = S.val[k];
-            if (c == row) d = v;
-            else rsum = __dadd_rn(rsum, __dmul_rn(v, XS ? xs[c] : __ldcg(x + c)));
+        if (XS) {
+          if (row < e) {
+            const int ks = S.rp[row - ra] - ka, ke = S.rp[row - ra + 1] - ka;
+            for (int k = ks + lane; k < ke; k += T) {
+              const int c = S.col[k];
+              const double v = S.val[k];
+              if (c == row) d = v;
+              else rsum = __dadd_rn(rsum, __dmul_rn(v, xs[c]));
+            }
+          }
+        } else {
+          // x through L2: all gathers of the row leave in one burst (one round trip per wavefront, not one per entry)
+          int ks = 0, ke = 0;
+          if (row < e) {
+            ks = S.rp[row - ra] - ka;
+            ke = S.rp[row - ra + 1] - ka;
+          }
+          int c[kGsPrefetch];
+          double v[kGsPrefetch], xv[kGsPrefetch];
+          const double* a[kGsPrefetch];
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j) {
+            const int k = ks + lane + j * T;
+            const bool in = k < ke;
+            c[j] = in ? S.col[k] : -1;
+            v[j] = in ? S.val[k] : 0.0;
+            a[j] = (in && c[j] != row) ? x + c[j] : &g_gs_zero;
+          }
+          ldcg_burst8(xv, a);
+          pin_burst8(xv, opaque_zero);
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j) {
+            if (c[j] == row && c[j] >= 0) d = v[j];
+            else rsum = __dadd_rn(rsum, __dmul_rn(v[j], xv[j]));
+          }
+          for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {
+            const int cc = S.col[k];
+            const double vv = S.val[k];
+            if (cc == row) d = vv;
+            else rsum = __dadd_rn(rsum, __dmul_rn(vv, __ldcg(x + cc)));
           }
         }
         if (T > 1) {
@@ -851,6 +885,7 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
           }
         if (need && poll_sleep) __nanosleep(poll_sleep);
       }
+      __syncwarp();   // lanes leave the poll loop at different times: reconverge before the arithmetic
       double rsum = 0.0, d = 0.0;
 #pragma unroll
       for (int j = 0; j < kGsPrefetch; ++j) {
@@ -876,10 +911,10 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
         }
         rsum = __dadd_rn(rsum, __dmul_rn(vv, xv));
       }
-      if (T > 1) {
-        const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << ((tid & 31) / T * T));
-        rsum = group_lanes_sum<T>(rsum, gmask);
-        d = group_lanes_sum<T>(d, gmask);
+      if (T > 1) {   // rows of a tile are independent (wavefront-aligned tiles): whole-warp shuffles cannot deadlock
+        __syncwarp();
+        rsum = group_lanes_sum<T>(rsum, 0xffffffffu);
+        d = group_lanes_sum<T>(d, 0xffffffffu);
       }
       if (active && lane == 0) {
         double xnew = xold;

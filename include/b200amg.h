@@ -205,11 +205,14 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
  * convergence-residual kernel (multilevel.jl:188-189) of every iteration with a CUDA event pair on
  * the launching stream; read the per-iteration milliseconds back with b200amg_residual_timings.
  * STREAM_CHUNK (default 1): consecutive tiles each CTA of the TMA stream kernels takes per run
- * (0 = one contiguous range per CTA).  GS_MODE (default 1): 1 = Gauss-Seidel/SOR as one persistent
- * dataflow kernel per sweep, 0 = one launch per wavefront.  Cycle graphs already captured keep the
- * values they were captured with. */
+ * (0 = one contiguous range per CTA).  GS_MODE (default 2) selects the Gauss-Seidel / SOR sweep:
+ * 0 one launch per wavefront, 1 wavefront-counter dataflow kernel, 2 TMA-fed per-row mailbox kernel
+ * on wide levels (mean wavefront >= GS_MAIL_MIN_WIDTH rows), one CTA on levels of <= GS_CTA_ROWS rows,
+ * counter kernel in between, 3 like 2 with the ticket mailbox kernel.  GS_ACQUIRE / GS_POLL_SLEEP /
+ * GS_GATE_SLEEP tune the hand-off.  Cycle graphs already captured keep the values they were captured with. */
 enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1, B200AMG_OPT_STREAM_CHUNK = 2, B200AMG_OPT_GS_MODE = 3, B200AMG_OPT_GS_ACQUIRE = 4, B200AMG_OPT_GS_POLL_SLEEP = 5,
-       B200AMG_OPT_GS_GATE_SLEEP = 6, B200AMG_OPT_GS_CTA_ROWS = 7 };
+       B200AMG_OPT_GS_GATE_SLEEP = 6, B200AMG_OPT_GS_CTA_ROWS = 7,
+       B200AMG_OPT_GS_MAIL_MIN_WIDTH = 8 };
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
 int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
 /* Diagnostics: run one dataflow Gauss-Seidel sweep (forward / backward) of `level` on the level's

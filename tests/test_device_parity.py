@@ -374,3 +374,29 @@ def test_properties_at_size(amg, jac):
     dev.smooth(0, 0, xx, b)
     assert np.abs(xx - xs).max() < 1e-4
     ml.release()
+
+
+# ---- every Gauss-Seidel sweep protocol gives the reference's sequential sweep ---------------------
+@pytest.mark.parametrize("mode,env", [(0, {}), (1, {}), (2, {}), (3, {}), (2, {"cta_rows": 0, "mail_width": 1})])
+def test_all_sweep_protocols_agree_with_oracle(amg, mode, env):
+    """gs_mode 0 one launch per wavefront, 1 wavefront-counter dataflow, 2 TMA-fed mailbox (+ single-CTA on small
+    levels), 3 ticket mailbox; the last case forces the mailbox sweeps onto every level."""
+    A = amg.poisson((28, 28, 28))
+    ml = amg.ruge_stuben(A)
+    dev = ml.device()
+    dev.set_option(0, 0)            # no graph replay: options take effect on every launch
+    dev.set_option(3, mode)
+    if "cta_rows" in env:
+        dev.set_option(7, env["cta_rows"])
+    if "mail_width" in env:
+        dev.set_option(8, env["mail_width"])
+    r = _rng(21)
+    for lv, level in enumerate(ml.levels):
+        x0, b = r.standard_normal(level.A.n), r.standard_normal(level.A.n)
+        x = dev.smooth(lv, 0, x0.copy(), b)
+        assert relinf(x, oracle.smooth(level.A, level.presmoother.config, x0.copy(), b)) <= TOL_SWEEP, (mode, lv)
+    b = r.random(A.n)
+    x = amg._solve(ml, b, maxiter=3, calculate_residual=False)
+    ref = oracle.OracleHierarchy(ml).solve(b, maxiter=3, calculate_residual=False)
+    assert relinf(x, ref) <= TOL_CYCLE
+    ml.release()
