@@ -87,6 +87,19 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(args, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the roofline kernel, from the committed ncu capture
+    (profiles/r01_ncu_traffic.json); only for the workload that capture was taken on."""
+    if not (world == 1 and args.size == 256 and args.dim == 3):
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+            t = json.load(f)["csr_stream_kernel<1,1>@poisson256"]
+        return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def build_problem(args):
     import algebraicmultigrid_jl_b200 as amg
 
@@ -292,7 +305,7 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
                 "avg_launch_ms": res_ms_avg, "launches_timed": int(len(res_ms)), "share_of_step": res_ms_avg / (ms / K),
-                "traffic": None}
+                "traffic": ncu_traffic(args, world)}
     phases = ["presmoother", "residual", "restriction", "coarse_solve", "prolongation", "postsmoother"]
     prof = dev.profile_cycle(0) if world == 1 else np.zeros((dev.nlevels, 6))
     infos = [dev.level_info(i) for i in range(dev.nlevels)]
