@@ -662,6 +662,7 @@ struct b200amg_hierarchy {
   bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
+  int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
@@ -793,36 +794,46 @@ static void launch_sweep_T(H* h, const DevCsr& A, const DevSchedule& sc, double*
     count_launch(h);
   }
 }
-template <int T, int BS>
+template <int T, int BS, bool MAIL>
 static int gs_dataflow_ctas() {   // co-resident CTAs of the persistent dataflow sweep
   static int cached = 0;
   if (!cached) {
     int per_sm = 0;
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_kernel<T, BS>, BS, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_kernel<T, BS, MAIL>, BS, 0));
     cached = std::max(1, per_sm) * kNumSM;
   }
   return cached;
 }
 template <int T, int BS>
-static void launch_dataflow_T(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
-  const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS>());
+static void launch_dataflow_T(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor,
+                              uint4* mail, unsigned* mail_ctl) {
   CUDA_OK(cudaMemsetAsync(sc.counters, 0, sizeof(unsigned) * (size_t)(sc.nlev + 2) * kGsCounterStride, h->stream));
-  gs_dataflow_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
-                                                       sc.backward, h->gs_acquire, h->opaque_zero, h->gs_debug);
+  if (mail && h->gs_counter_mail && !h->gs_debug) {
+    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, true>());
+    gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(mail_ctl);   // new epoch for the mailbox flags
+    count_launch(h);
+    gs_dataflow_kernel<T, BS, true><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
+                                                               sc.backward, h->gs_acquire, h->opaque_zero, nullptr, mail, mail_ctl);
+  } else {
+    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, false>());
+    gs_dataflow_kernel<T, BS, false><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
+                                                                sc.backward, h->gs_acquire, h->opaque_zero, h->gs_debug, nullptr, nullptr);
+  }
   count_launch(h);
 }
-static void launch_dataflow(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+static void launch_dataflow(H* h, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w, int sor,
+                            uint4* mail = nullptr, unsigned* mail_ctl = nullptr) {
   if (sc.ntasks == 0) return;
 #define B200AMG_DF_CASE(TT)                                                    \
   case TT:                                                                     \
-    if (sc.df_threads == 128) launch_dataflow_T<TT, 128>(h, A, sc, x, b, w, sor); \
-    else launch_dataflow_T<TT, 256>(h, A, sc, x, b, w, sor);                      \
+    if (sc.df_threads == 128) launch_dataflow_T<TT, 128>(h, A, sc, x, b, w, sor, mail, mail_ctl); \
+    else launch_dataflow_T<TT, 256>(h, A, sc, x, b, w, sor, mail, mail_ctl);                      \
     break;
   switch (sc.df_lanes) {
     B200AMG_DF_CASE(1) B200AMG_DF_CASE(2) B200AMG_DF_CASE(4) B200AMG_DF_CASE(8) B200AMG_DF_CASE(16)
     default:
-      if (sc.df_threads == 128) launch_dataflow_T<32, 128>(h, A, sc, x, b, w, sor);
-      else launch_dataflow_T<32, 256>(h, A, sc, x, b, w, sor);
+      if (sc.df_threads == 128) launch_dataflow_T<32, 128>(h, A, sc, x, b, w, sor, mail, mail_ctl);
+      else launch_dataflow_T<32, 256>(h, A, sc, x, b, w, sor, mail, mail_ctl);
   }
 #undef B200AMG_DF_CASE
 }
@@ -945,7 +956,7 @@ static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, d
   // but 6-7 with several lanes per row, where the ticket mailbox sweep does 3.0-4.7 and the counter sweep 4.6-6.0
   if (h->gs_mode == 2 && M.mail && M.gs_ntiles > 0 && wide && (M.gs_lanes == 1 || h->gs_tile_any_lanes)) { launch_gs_tile(h, M, A, sc, x, b, w, sor); return; }
   if (h->gs_mode >= 2 && M.mail && wide) { launch_mail(h, M, A, sc, x, b, w, sor); return; }
-  if (h->gs_mode >= 1) { launch_dataflow(h, A, sc, x, b, w, sor); return; }
+  if (h->gs_mode >= 1) { launch_dataflow(h, A, sc, x, b, w, sor, M.mail, M.mail_ctl); return; }
   switch (A.lanes) {
     case 2: launch_sweep_T<2>(h, A, sc, x, b, w, sor); break;
     case 4: launch_sweep_T<4>(h, A, sc, x, b, w, sor); break;
@@ -1427,6 +1438,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_cta_rows = env_int("B200AMG_GS_CTA_ROWS", 12288);
   h->gs_mail_min_width = env_int("B200AMG_GS_MAIL_MIN_WIDTH", 1024);
   h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 1);
+  h->gs_counter_mail = env_int("B200AMG_GS_COUNTER_MAIL", 1);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);

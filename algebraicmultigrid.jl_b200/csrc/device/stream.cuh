@@ -298,15 +298,44 @@ __device__ __forceinline__ void pin_burst8(double (&v)[kGsPrefetch], int opaque_
   for (int j = 0; j < kGsPrefetch; ++j) v[j] = __hiloint2double(__double2hiint(v[j]) | dep, __double2loint(v[j]));
 }
 
+__device__ __forceinline__ void st_mail(uint4* p, double v, unsigned e) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(e),
+               "r"((unsigned)__double2hiint(v)), "r"(e)
+               : "memory");
+}
+// eight mailbox polls issued back to back
+__device__ __forceinline__ void ld_mail8(uint4 (&m)[8], const uint4* const (&a)[8]) {
+  asm volatile(
+      "ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%4, %5, %6, %7}, [%33];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%8, %9, %10, %11}, [%34];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%12, %13, %14, %15}, [%35];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%16, %17, %18, %19}, [%36];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%20, %21, %22, %23}, [%37];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%24, %25, %26, %27}, [%38];\n\t"
+      "ld.relaxed.gpu.global.v4.u32 {%28, %29, %30, %31}, [%39];"
+      : "=r"(m[0].x), "=r"(m[0].y), "=r"(m[0].z), "=r"(m[0].w), "=r"(m[1].x), "=r"(m[1].y), "=r"(m[1].z), "=r"(m[1].w),
+        "=r"(m[2].x), "=r"(m[2].y), "=r"(m[2].z), "=r"(m[2].w), "=r"(m[3].x), "=r"(m[3].y), "=r"(m[3].z), "=r"(m[3].w),
+        "=r"(m[4].x), "=r"(m[4].y), "=r"(m[4].z), "=r"(m[4].w), "=r"(m[5].x), "=r"(m[5].y), "=r"(m[5].z), "=r"(m[5].w),
+        "=r"(m[6].x), "=r"(m[6].y), "=r"(m[6].z), "=r"(m[6].w), "=r"(m[7].x), "=r"(m[7].y), "=r"(m[7].z), "=r"(m[7].w)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
+      : "memory");
+}
 // tasks[t] = {first row, rows, wavefront in sweep order, tasks of the previous wavefront}
 // counters[0] = ticket, counters[(1 + w) * kGsCounterStride] = finished tasks of wavefront w (zeroed before the launch)
-template <int T, int BS>
+// MAIL: rows are additionally published as 16-byte {value, epoch} mailboxes (see gs_mail_kernel) and the
+// earlier-ordered neighbours are read from there.  The flags vouch for the data, so the producer needs NO
+// fence between its stores and the completion count (0.4 us off every hop); a mailbox that is not visible
+// yet when the count is, is simply polled again.
+template <int T, int BS, bool MAIL>
 __global__ void __launch_bounds__(BS)
     gs_dataflow_kernel(int ntasks, const int4* __restrict__ tasks, unsigned* counters, const int* __restrict__ rowptr,
                        const int* __restrict__ col, const double* __restrict__ val, double* x, const double* __restrict__ b,
-                       double omega, int sor, int backward, int acquire_mode, int opaque_zero, unsigned long long* dbg) {
+                       double omega, int sor, int backward, int acquire_mode, int opaque_zero, unsigned long long* dbg,
+                       uint4* mail, const unsigned* mail_ctl) {
   __shared__ int s_task[2];
   const int tid = threadIdx.x, g = tid / T, lane = tid % T;
+  const unsigned e = MAIL ? ld_relaxed_u32(mail_ctl + 1) : 0u;
   if (tid == 0) s_task[0] = (int)atomicAdd(&counters[0], 1u);
   __syncthreads();
   int cur = s_task[0], buf = 0;
@@ -323,7 +352,7 @@ __global__ void __launch_bounds__(BS)
       ke = __ldg(rowptr + row + 1);
       if (lane == 0) {
         bv = __ldg(b + row);
-        if (sor) xold = __ldcg(x + row);   // only this row's own update ever writes x[row] during the sweep
+        if (sor || MAIL) xold = __ldcg(x + row);   // only this row's own update ever writes x[row] during the sweep
       }
     }
     int c[kGsPrefetch];
@@ -375,8 +404,39 @@ __global__ void __launch_bounds__(BS)
         const bool earlier = c[j] >= 0 && (backward ? c[j] > row : c[j] < row);
         a[j] = earlier ? x + c[j] : &g_gs_zero;
       }
-      ldcg_burst8(xe, a);
-      pin_burst8(xe, opaque_zero);
+      if (!MAIL) {
+        ldcg_burst8(xe, a);
+        pin_burst8(xe, opaque_zero);
+      } else {
+        unsigned need = 0u;
+#pragma unroll
+        for (int j = 0; j < kGsPrefetch; ++j) {
+          xe[j] = 0.0;
+          if (a[j] != &g_gs_zero) need |= 1u << j;
+        }
+        while (need) {
+          const uint4* ma[kGsPrefetch];
+          uint4 mm[kGsPrefetch];
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j) ma[j] = ((need >> j) & 1u) ? mail + c[j] : mail + (row >= 0 ? row : 0);
+          ld_mail8(mm, ma);
+          {
+            unsigned dep = mm[0].y;
+#pragma unroll
+            for (int j = 1; j < kGsPrefetch; ++j) dep &= mm[j].y;
+            dep &= (unsigned)opaque_zero;
+#pragma unroll
+            for (int j = 0; j < kGsPrefetch; ++j) mm[j].y |= dep;
+          }
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j)
+            if (((need >> j) & 1u) && mm[j].y == e && mm[j].w == e) {
+              xe[j] = __hiloint2double((int)mm[j].z, (int)mm[j].x);
+              need &= ~(1u << j);
+            }
+        }
+        __syncwarp();
+      }
     }
     if (dbg && tid == 0) dbg[(size_t)cur * 8 + 1] = global_ns() + (unsigned long long)(__double2loint(xe[0]) & opaque_zero);
     double rsum = 0.0, d = 0.0;
@@ -391,14 +451,37 @@ __global__ void __launch_bounds__(BS)
     for (int k = ks + lane + kGsPrefetch * T; k < ke; k += T) {   // rows longer than T * kGsPrefetch
       const int cc = __ldg(col + k);
       const double vv = __ldg(val + k);
-      if (cc == row) d = vv;
-      else rsum = __dadd_rn(rsum, __dmul_rn(vv, __ldcg(x + cc)));
+      if (cc == row) { d = vv; continue; }
+      double xv;
+      if (MAIL && (backward ? cc > row : cc < row)) {
+        uint4 q;
+        do {
+          asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                       : "l"(mail + cc)
+                       : "memory");
+        } while (q.y != e || q.w != e);
+        xv = __hiloint2double((int)q.z, (int)q.x);
+      } else {
+        xv = __ldcg(x + cc);
+      }
+      rsum = __dadd_rn(rsum, __dmul_rn(vv, xv));
     }
     if (T > 1) {
       rsum = lanes_sum<T>(rsum);
       d = lanes_sum<T>(d);
     }
-    if (active && lane == 0 && d != 0.0) {
+    if (MAIL) {
+      if (active && lane == 0) {
+        double xnew = xold;
+        if (d != 0.0) {
+          const double r = __dsub_rn(bv, rsum);
+          xnew = sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d);
+        }
+        st_mail(mail + row, xnew, e);
+        __stcg(x + row, xnew);
+      }
+    } else if (active && lane == 0 && d != 0.0) {
       const double r = __dsub_rn(bv, rsum);
       __stcg(x + row, sor ? __dadd_rn(__dmul_rn(1.0 - omega, xold), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d));
     }
@@ -406,7 +489,7 @@ __global__ void __launch_bounds__(BS)
     __syncthreads();
     if (tid == 0) {
       if (dbg) dbg[(size_t)cur * 8 + 5] = global_ns();
-      __threadfence();   // release side: every row of this task (bar.sync above) is visible before the count
+      if (!MAIL) __threadfence();   // release side: every row of this task (bar.sync above) is visible before the count
       if (dbg) dbg[(size_t)cur * 8 + 6] = global_ns();
       red_relaxed_inc(counters + (size_t)(1 + tk.z) * kGsCounterStride);
       if (dbg) dbg[(size_t)cur * 8 + 7] = global_ns();
@@ -444,11 +527,6 @@ __global__ void gs_mail_prepare_kernel(unsigned* ctl) {
     ctl[0] = 0u;
     ctl[1] = ctl[1] + 1u;
   }
-}
-__device__ __forceinline__ void st_mail(uint4* p, double v, unsigned e) {
-  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(e),
-               "r"((unsigned)__double2hiint(v)), "r"(e)
-               : "memory");
 }
 // four mailbox polls issued back to back
 __device__ __forceinline__ void ld_mail4(uint4 (&m)[4], const uint4* const (&a)[4]) {
@@ -757,24 +835,6 @@ __global__ void __launch_bounds__(kGsCtaThreads, 1)
 // =============================================================================================
 constexpr int kGsTileThreads = 256;
 
-// eight mailbox polls issued back to back
-__device__ __forceinline__ void ld_mail8(uint4 (&m)[8], const uint4* const (&a)[8]) {
-  asm volatile(
-      "ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%4, %5, %6, %7}, [%33];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%8, %9, %10, %11}, [%34];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%12, %13, %14, %15}, [%35];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%16, %17, %18, %19}, [%36];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%20, %21, %22, %23}, [%37];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%24, %25, %26, %27}, [%38];\n\t"
-      "ld.relaxed.gpu.global.v4.u32 {%28, %29, %30, %31}, [%39];"
-      : "=r"(m[0].x), "=r"(m[0].y), "=r"(m[0].z), "=r"(m[0].w), "=r"(m[1].x), "=r"(m[1].y), "=r"(m[1].z), "=r"(m[1].w),
-        "=r"(m[2].x), "=r"(m[2].y), "=r"(m[2].z), "=r"(m[2].w), "=r"(m[3].x), "=r"(m[3].y), "=r"(m[3].z), "=r"(m[3].w),
-        "=r"(m[4].x), "=r"(m[4].y), "=r"(m[4].z), "=r"(m[4].w), "=r"(m[5].x), "=r"(m[5].y), "=r"(m[5].z), "=r"(m[5].w),
-        "=r"(m[6].x), "=r"(m[6].y), "=r"(m[6].z), "=r"(m[6].w), "=r"(m[7].x), "=r"(m[7].y), "=r"(m[7].z), "=r"(m[7].w)
-      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
-      : "memory");
-}
 template <int T>
 __device__ __forceinline__ double group_lanes_sum(double v, unsigned mask) {
 #pragma unroll
