@@ -10,3 +10,70 @@ def poisson(sz):
     else:
         dims = tuple(int(s) for s in sz)
     return _hostlib.poisson(dims)
+
+
+def elasticity_2d(nx, ny, E=1.0, nu=0.3):
+    """Synthetic plane-strain linear elasticity on an ``nx x ny`` grid of unit Q1 (bilinear) elements, clamped on
+    the edge x = 0 — the structured-grid analogue of the reference's only elasticity input, the 208-dof fixture
+    ``test/lin_elastic_2d.jld2`` (``test/nns_test.jl:213-223``; the reference ships no generator).
+    Returns ``(A, b, B)``: the SPD stiffness matrix on the free dofs (u, v interleaved per node, node index = i + (nx+1) j
+    minus the clamped nodes), a right-hand side (unit downward traction on the edge x = nx) and the three rigid-body
+    modes ``[1 0 -y; 0 1 x]`` restricted to the free dofs — the near-null-space ``B`` of ``smoothed_aggregation(A; B=B)``,
+    laid out as ``create_nns_frame`` does for the beam (``test/nns_test.jl:138-164``)."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    from .sparse import SparseMatrixCSC
+
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    D = np.array([[lam + 2 * mu, lam, 0.0], [lam, lam + 2 * mu, 0.0], [0.0, 0.0, mu]])
+    # 8 x 8 element matrix of the unit square, 2 x 2 Gauss points
+    gp = np.array([-1.0, 1.0]) / np.sqrt(3.0)
+    xi_n = np.array([-1.0, 1.0, 1.0, -1.0])
+    eta_n = np.array([-1.0, -1.0, 1.0, 1.0])
+    Ke = np.zeros((8, 8))
+    for xi in gp:
+        for eta in gp:
+            dN_dxi = 0.25 * xi_n * (1 + eta_n * eta)
+            dN_deta = 0.25 * eta_n * (1 + xi_n * xi)
+            dNx, dNy = 2.0 * dN_dxi, 2.0 * dN_deta          # unit element: d/dx = 2 d/dxi
+            Bm = np.zeros((3, 8))
+            Bm[0, 0::2] = dNx
+            Bm[1, 1::2] = dNy
+            Bm[2, 0::2] = dNy
+            Bm[2, 1::2] = dNx
+            Ke += 0.25 * (Bm.T @ D @ Bm)                      # det J = 1/4, weights 1
+    Ke = 0.5 * (Ke + Ke.T)
+    nnx, nny = nx + 1, ny + 1
+    ii, jj = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    n0 = (ii + nnx * jj).ravel()
+    nodes = np.stack([n0, n0 + 1, n0 + 1 + nnx, n0 + nnx], axis=1)          # counter-clockwise
+    dofs = np.empty((nodes.shape[0], 8), dtype=np.int64)
+    dofs[:, 0::2] = 2 * nodes
+    dofs[:, 1::2] = 2 * nodes + 1
+    rows = np.repeat(dofs, 8, axis=1).ravel()
+    cols = np.tile(dofs, (1, 8)).ravel()
+    vals = np.tile(Ke.ravel(), nodes.shape[0])
+    ndof = 2 * nnx * nny
+    K = sp.coo_matrix((vals, (rows, cols)), shape=(ndof, ndof)).tocsc()
+    node_i = np.arange(nnx * nny) % nnx
+    free_nodes = np.nonzero(node_i != 0)[0]
+    free = np.empty(2 * free_nodes.size, dtype=np.int64)
+    free[0::2] = 2 * free_nodes
+    free[1::2] = 2 * free_nodes + 1
+    A = K[free][:, free].tocsc()
+    A.sort_indices()
+    x = (free_nodes % nnx).astype(np.float64)
+    y = (free_nodes // nnx).astype(np.float64)
+    B = np.zeros((free.size, 3))
+    B[0::2, 0] = 1.0
+    B[1::2, 1] = 1.0
+    B[0::2, 2] = -y
+    B[1::2, 2] = x
+    f = np.zeros(ndof)
+    edge = np.nonzero(node_i == nx)[0]
+    w = np.ones(edge.size)
+    w[[0, -1]] = 0.5
+    f[2 * edge + 1] = -w / ny
+    return SparseMatrixCSC.from_scipy(A), f[free], B

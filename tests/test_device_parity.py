@@ -400,3 +400,85 @@ def test_all_sweep_protocols_agree_with_oracle(amg, mode, env):
     ref = oracle.OracleHierarchy(ml).solve(b, maxiter=3, calculate_residual=False)
     assert relinf(x, ref) <= TOL_CYCLE
     ml.release()
+
+
+# ---- BASELINE.json's full size (config C3: 256^3, RS, default symmetric Gauss-Seidel): properties only ----
+def test_full_size_256_properties(amg):
+    n1 = 256
+    A = amg.poisson((n1, n1, n1))
+    n = A.n
+    assert n == 16777216 and A.nnz == 117047296
+    ml = amg.ruge_stuben(A)
+    dev = ml.device()
+    r = _rng(256)
+    x = r.standard_normal(n)
+    # SpMV against the closed-form 7-point stencil (first index fastest, gallery.jl:5-63)
+    ax = dev.apply(0, 0, np.empty(n), x)
+    X = x.reshape(n1, n1, n1)
+    st = 6 * X
+    for ax_ in range(3):
+        lo, hi = [slice(None)] * 3, [slice(None)] * 3
+        lo[ax_], hi[ax_] = slice(0, -1), slice(1, None)
+        st[tuple(hi)] -= X[tuple(lo)]
+        st[tuple(lo)] -= X[tuple(hi)]
+    assert relinf(ax, st.reshape(-1)) <= TOL_KERNEL
+    del X, st
+    # R = P' on the fine level
+    nc = ml.levels[0].R.shape[0]
+    e = r.standard_normal(nc)
+    Rr, Pe = dev.apply(0, 2, np.empty(nc), x), dev.apply(0, 1, np.empty(n), e)
+    assert abs(Rr @ e - x @ Pe) <= 1e-10 * abs(x @ Pe)
+    # one exact-order symmetric Gauss-Seidel sweep on the fine level: x = ones is a fixed point for b = A*ones, and the
+    # sweep is a contraction in the energy norm for any start (SPD matrix)
+    b = A.matvec(np.ones(n))
+    ones = np.ones(n)
+    assert np.abs(dev.smooth(0, 0, ones.copy(), b) - 1.0).max() <= 1e-13
+    y = dev.smooth(0, 0, x.copy(), b)
+    err0, err1 = x - 1.0, y - 1.0
+    e0 = err0 @ dev.apply(0, 0, np.empty(n), err0)
+    e1 = err1 @ dev.apply(0, 0, np.empty(n), err1)
+    assert 0 < e1 < e0
+    # the solve converges to the known solution with a strictly decreasing residual history
+    xs, hist = amg._solve(ml, b, log=True, maxiter=60)
+    assert hist[-1] <= np.sqrt(np.finfo(float).eps) * hist[0] and np.all(np.diff(hist) < 0)
+    assert np.abs(xs - 1).max() < 1e-3
+    rr = dev.residual(0, np.empty(n), b, xs)
+    assert abs(np.linalg.norm(rr) - hist[-1]) <= 1e-9 * hist[0]
+    ml.release()
+
+
+def test_block_right_hand_sides(amg):
+    # bs > 1 workspaces (multilevel.jl:28-59): columns share one Frobenius-norm convergence test
+    A = amg.poisson((30, 30))
+    ml = amg.ruge_stuben(A)
+    B = _rng(31).random((A.n, 3))
+    X, hist = amg._solve(ml, B, log=True, reltol=1e-10)
+    assert X.shape == B.shape
+    H = oracle.OracleHierarchy(ml)
+    Xr = np.zeros_like(B)
+    histr = [np.linalg.norm(B)]
+    tol = 1e-10 * histr[0]
+    while len(histr) <= 100 and histr[-1] > tol:
+        for j in range(3):
+            Xr[:, j] = H.cycle(Xr[:, j].copy(), B[:, j])
+        histr.append(np.linalg.norm(B - np.column_stack([A.matvec(Xr[:, j]) for j in range(3)])))
+    assert len(hist) == len(histr) and np.allclose(hist, histr, rtol=TOL_HIST)
+    assert np.linalg.norm(X - Xr) <= TOL_SOLVE_X * np.linalg.norm(Xr)
+    ml.release()
+
+
+def test_synthetic_elasticity_with_near_null_space(amg):
+    # the reference's elasticity behaviour (test/nns_test.jl:214-223) on the synthetic generator: SA with the rigid-body
+    # modes converges and is a good CG preconditioner; the device PCG matches the oracle PCG
+    A, b, B = amg.elasticity_2d(40, 24)
+    ml = amg.smoothed_aggregation(A, B=B)
+    H = oracle.OracleHierarchy(ml)
+    x, hist = amg._solve(ml, b, log=True, reltol=1e-10)
+    xr, histr = H.solve(b, log=True, reltol=1e-10)
+    assert len(hist) == len(histr) and len(hist) < 100
+    assert np.linalg.norm(x - xr) <= TOL_SOLVE_X * np.linalg.norm(xr)
+    xc, info = amg.cg(A, b, Pl=amg.aspreconditioner(ml), reltol=1e-10, log=True)
+    xcr = H.pcg(b, reltol=1e-10)
+    assert info["iters"] == H.iters and np.linalg.norm(xc - xcr) <= 1e-8 * np.linalg.norm(xcr)
+    assert np.linalg.norm(A.matvec(xc) - b) <= 1e-9 * np.linalg.norm(b)
+    ml.release()
