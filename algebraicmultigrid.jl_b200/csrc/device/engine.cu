@@ -319,6 +319,7 @@ struct DevCsr {
   int4* meta = nullptr;
   int ntiles = 0;
   int stream_lanes = 1;
+  int stream_burst = 8;
   bool owner = false;
   void upload(const HostCsr& h) {
     nrows = h.nrows; ncols = h.ncols; nnz = h.nnz();
@@ -340,6 +341,7 @@ struct DevCsr {
     stream_lanes = 1;
     while (stream_lanes < 32 && mean > 12.0 * stream_lanes) stream_lanes *= 2;
     stream_lanes = env_int("B200AMG_STREAM_LANES", stream_lanes);
+    stream_burst = ((stream_lanes == 2 || stream_lanes == 4) && env_int("B200AMG_STREAM_BURST16", 1)) ? 16 : 8;
     const int G = kStreamThreads / stream_lanes;
     int passes = (int)(kTileNnz / std::max(1.0, G * std::max(mean, 1.0)));
     passes = std::min(std::max(passes, 1), 2);   // the kernel prefetches the epilogue operands of two passes
@@ -710,6 +712,8 @@ static void stream_set_attr() {
 }
 template <int MODE>
 static void stream_set_attr_all() {
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<2, MODE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<4, MODE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
   stream_set_attr<1, MODE>(); stream_set_attr<2, MODE>(); stream_set_attr<4, MODE>();
   stream_set_attr<8, MODE>(); stream_set_attr<16, MODE>(); stream_set_attr<32, MODE>();
 }
@@ -726,6 +730,16 @@ static void launch_stream(H* h, const DevCsr& A, const double* x, const double* 
     csr_stream_kernel<TT, MODE><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, \
                                                                                       A.val, x, b, y, omega, diagvals); \
     break;
+  if (A.stream_burst == 16) {   // 13-64 entries per row: two / four lanes, one burst of 16 gathers each
+    if (A.stream_lanes == 2)
+      csr_stream_kernel<2, MODE, 16><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, A.val,
+                                                                                           x, b, y, omega, diagvals);
+    else
+      csr_stream_kernel<4, MODE, 16><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, A.val,
+                                                                                           x, b, y, omega, diagvals);
+    count_launch(h);
+    return;
+  }
   switch (A.stream_lanes) {
     B200AMG_STREAM_CASE(1) B200AMG_STREAM_CASE(2) B200AMG_STREAM_CASE(4) B200AMG_STREAM_CASE(8) B200AMG_STREAM_CASE(16)
     default:

@@ -29,7 +29,7 @@ constexpr int kStreamThreads = 256;
 constexpr int kTileNnz = 2048;
 constexpr int kTileRowsMax = 1024;
 constexpr int kStages = 3;
-constexpr int kStreamBurst = 8;   // x gathers a lane issues back to back for a short row
+constexpr int kStreamBurst = 8;   // x gathers a lane issues back to back for a short row (template default)
 
 struct __align__(16) StreamStage {
   double val[kTileNnz + 8];
@@ -92,7 +92,7 @@ __device__ __forceinline__ int stream_tile_of(int i, int chunk) {
   return (i / chunk) * ((int)gridDim.x * chunk) + (int)blockIdx.x * chunk + (i % chunk);
 }
 
-template <int T, int MODE>
+template <int T, int MODE, int BURST = kStreamBurst>
 __global__ void __launch_bounds__(kStreamThreads, 2)
     csr_stream_kernel(int ntiles, int chunk, const int4* __restrict__ meta, const int* __restrict__ rowptr,
                       const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
@@ -148,27 +148,27 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
       if (r < nrows) {
         const int ks = S.rp[rofs + r] - ka, ke = S.rp[rofs + r + 1] - ka;
         const int row = m.x + r;
-        if (ke - ks <= kStreamBurst * T) {
+        if (ke - ks <= BURST * T) {
           // short row (every stencil row): ALL its x gathers leave in one burst, so the row costs one L2
           // round trip; the products are then added in the reference's order (idle slots add an exact +0,
           // as the reference itself does for the diagonal in smooth!: `rsum += ifelse(row == i, z, ...)`)
-          int c[kStreamBurst];
-          double v[kStreamBurst], xv[kStreamBurst];
+          int c[BURST];
+          double v[BURST], xv[BURST];
 #pragma unroll
-          for (int j = 0; j < kStreamBurst; ++j) {
+          for (int j = 0; j < BURST; ++j) {
             const int k = ks + lane + j * T;
             const bool in = k < ke;
             c[j] = in ? S.col[k] : -1;
             v[j] = in ? S.val[k] : 0.0;
           }
 #pragma unroll
-          for (int j = 0; j < kStreamBurst; ++j) {
+          for (int j = 0; j < BURST; ++j) {
             const bool use = c[j] >= 0 && !(MODE == 3 && c[j] == row);
             xv[j] = use ? __ldg(x + c[j]) : 0.0;
             if (MODE == 3 && c[j] == row) diag = v[j];
           }
 #pragma unroll
-          for (int j = 0; j < kStreamBurst; ++j) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
+          for (int j = 0; j < BURST; ++j) sum = __dadd_rn(sum, __dmul_rn(v[j], xv[j]));
         } else {
 #pragma unroll 4
           for (int k = ks + lane; k < ke; k += T) {
