@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "stream.cuh"
 #include "partition.h"
+#include "cluster_gs.cuh"
 
 using namespace b200amg;
 
@@ -664,6 +665,10 @@ struct b200amg_hierarchy {
   bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
+  int gs_cluster = 0;                 // one-cluster sweep (x in distributed shared memory) for mid-size levels: measured
+                                      // 2.4-3.9 us per wavefront vs 2.2-2.5 for the counter sweep, so off by default
+  int64_t gs_cluster_rows = 380000;
+  int gs_cluster_log_nc = 3, gs_cluster_threads = 256;
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
@@ -920,6 +925,51 @@ static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const
     default: launch_gs_tile_T<32>(h, M, A, sc, x, b, w, sor); break;
   }
 }
+// ---- one-cluster sweep for mid-size levels (cluster_gs.cuh) ----
+template <int LOG_NC, int BS>
+static bool launch_gs_cluster_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b,
+                                double w, int sor) {
+  constexpr int NC = 1 << LOG_NC;
+  const size_t smem = (size_t)((M.n + NC - 1) / NC) * sizeof(double) + (size_t)(M.nlev + 1) * sizeof(int) + 16;
+  static int state = 0;   // 0 unknown, 1 usable, -1 not schedulable on this device
+  if (state < 0 || smem > 200 * 1024) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NC, 1, 1);
+  cfg.blockDim = dim3(BS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (state == 0) {
+    int nclusters = 0;
+    if (cudaFuncSetAttribute(gs_cluster_kernel<LOG_NC, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        (NC > 8 && cudaFuncSetAttribute(gs_cluster_kernel<LOG_NC, BS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+        cudaOccupancyMaxActiveClusters(&nclusters, gs_cluster_kernel<LOG_NC, BS>, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      state = -1;
+      return false;
+    }
+    state = 1;
+  }
+  CUDA_OK(cudaLaunchKernelEx(&cfg, gs_cluster_kernel<LOG_NC, BS>, (int)M.n, M.nlev, (const int*)M.d_fwd_lvlptr, (const int*)A.ptr,
+                             (const int*)A.idx, (const double*)A.val, x, b, w, sor, sc.backward));
+  count_launch(h);
+  return true;
+}
+static bool launch_gs_cluster(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                              int sor) {
+  const int nc = h->gs_cluster_log_nc, bs = h->gs_cluster_threads;
+#define B200AMG_CL(LN, BSZ) if (nc == LN && bs == BSZ && launch_gs_cluster_T<LN, BSZ>(h, M, A, sc, x, b, w, sor)) return true;
+  B200AMG_CL(1, 1024) B200AMG_CL(2, 1024) B200AMG_CL(3, 1024) B200AMG_CL(4, 1024)
+  B200AMG_CL(1, 256) B200AMG_CL(2, 256) B200AMG_CL(3, 256) B200AMG_CL(4, 256)
+#undef B200AMG_CL
+  return launch_gs_cluster_T<4, 1024>(h, M, A, sc, x, b, w, sor);
+}
 constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
 template <int T, bool XS>
 static void gs_cta_set_attr() {
@@ -966,6 +1016,10 @@ static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, d
   // wavefront-counter sweep in between.
   if (h->gs_mode >= 1 && M.n <= h->gs_cta_rows && A.ntiles > 0 && M.d_fwd_lvlptr) { launch_gs_cta(h, M, A, sc, x, b, w, sor); return; }
   const bool wide = sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width;
+  // mid-size level with long rows and narrow wavefronts: one cluster, x in distributed shared memory
+  if (h->gs_mode >= 1 && h->gs_cluster && !wide && M.d_fwd_lvlptr && M.n <= h->gs_cluster_rows && A.nrows > 0 &&
+      (double)A.nnz / (double)A.nrows >= 16.0 && launch_gs_cluster(h, M, A, sc, x, b, w, sor))
+    return;
   // measured, 256^3 RS hierarchy (us per wavefront): TMA-fed mailbox sweep 2.3 at one thread per row (stencil rows)
   // but 6-7 with several lanes per row, where the ticket mailbox sweep does 3.0-4.7 and the counter sweep 4.6-6.0
   if (h->gs_mode == 2 && M.mail && M.gs_ntiles > 0 && wide && (M.gs_lanes == 1 || h->gs_tile_any_lanes)) { launch_gs_tile(h, M, A, sc, x, b, w, sor); return; }
@@ -1453,6 +1507,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_mail_min_width = env_int("B200AMG_GS_MAIL_MIN_WIDTH", 1024);
   h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 1);
   h->gs_counter_mail = env_int("B200AMG_GS_COUNTER_MAIL", 1);
+  h->gs_cluster = env_int("B200AMG_GS_CLUSTER", 0);
+  h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
@@ -2140,6 +2196,9 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_POLL_SLEEP: h->gs_poll_sleep = (int)value; break;
     case B200AMG_OPT_GS_CTA_ROWS: h->gs_cta_rows = (int64_t)value; break;
     case B200AMG_OPT_GS_MAIL_MIN_WIDTH: h->gs_mail_min_width = (int64_t)value; break;
+    case B200AMG_OPT_GS_CLUSTER: h->gs_cluster = (int)value; break;
+    case 10: h->gs_cluster_log_nc = (int)value; break;     // experiment knobs (tools/tune_kernels.py)
+    case 11: h->gs_cluster_threads = (int)value; break;
     case B200AMG_OPT_GS_GATE_SLEEP: h->gs_gate_sleep = (int)value; break;
     default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown option %d", option);
   }

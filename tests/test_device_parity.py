@@ -482,3 +482,24 @@ def test_synthetic_elasticity_with_near_null_space(amg):
     assert info["iters"] == H.iters and np.linalg.norm(xc - xcr) <= 1e-8 * np.linalg.norm(xcr)
     assert np.linalg.norm(A.matvec(xc) - b) <= 1e-9 * np.linalg.norm(b)
     ml.release()
+
+
+def test_cluster_sweep_on_mid_size_level(amg):
+    """The optional one-cluster sweep (x in distributed shared memory, cluster_gs.cuh; off by default because it measured
+    no faster than the counter sweep) must give the reference's sequential sweep for every cluster shape."""
+    ml = amg.ruge_stuben(amg.poisson((48, 48, 48)))
+    lv = 1
+    level = ml.levels[lv]
+    assert 12288 < level.A.n <= 380000 and level.A.nnz / level.A.n >= 16
+    dev = ml.device()
+    dev.set_option(0, 0)
+    r = _rng(48)
+    x0, b = r.standard_normal(level.A.n), r.standard_normal(level.A.n)
+    ref = oracle.smooth(level.A, level.presmoother.config, x0.copy(), b)
+    for cluster, lognc, threads in ((1, 3, 256), (1, 4, 1024), (1, 1, 1024), (0, 3, 256)):
+        dev.set_option(9, cluster)
+        dev.set_option(10, lognc)
+        dev.set_option(11, threads)
+        x = dev.smooth(lv, 0, x0.copy(), b)
+        assert relinf(x, ref) <= TOL_SWEEP, (cluster, lognc, threads)
+    ml.release()

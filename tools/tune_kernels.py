@@ -80,3 +80,14 @@ if args.smoother == "gs" and os.environ.get("SWEEP_CTA"):
             ms = dev.time_kernel(lv, 2, reps=3)
             row.append(round(1e3 * ms / max(2 * info["wavefronts"], 1), 2))
         print(json.dumps({"cta_rows": cta_rows, "us_per_wavefront_by_level": row}), flush=True)
+if args.smoother == "gs" and os.environ.get("SWEEP_CLUSTER"):
+    dev.set_option(3, 2)
+    for lognc, bs in ((1, 1024), (2, 1024), (3, 1024), (4, 1024), (2, 256), (3, 256), (4, 256)):
+        dev.set_option(10, lognc)
+        dev.set_option(11, bs)
+        row = {}
+        for lv in (3, 4):
+            info = dev.level_info(lv)
+            ms = dev.time_kernel(lv, 2, reps=3)
+            row[lv] = round(1e3 * ms / max(2 * info["wavefronts"], 1), 2)
+        print(json.dumps({"cluster_ctas": 1 << lognc, "threads": bs, "us_per_wavefront": row}), flush=True)
