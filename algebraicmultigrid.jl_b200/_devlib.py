@@ -219,9 +219,11 @@ class DeviceHierarchy:
         keep = []
         try:
             if partition is not None:
-                rank, world, uid = partition
+                rank, world, uid = partition[:3]
                 buf = (C.c_char * len(uid)).from_buffer_copy(uid)
                 _check(L.b200amg_set_partition(self._h, rank, world, C.cast(buf, C.c_void_p), len(uid)))
+                if len(partition) > 3 and partition[3] != 1:
+                    _check(L.b200amg_set_option(self._h, 12, float(partition[3])))      # B200AMG_OPT_PART_LEVELS
             for lv in ml.levels:
                 a, p, r = csc_desc(lv.A, keep), csc_desc(lv.P, keep), csc_desc(lv.R, keep)
                 pre, post = smoother_desc(lv.presmoother.config), smoother_desc(lv.postsmoother.config)

@@ -623,6 +623,13 @@ struct Part {
   double *cb = nullptr, *cx = nullptr;   // my coarse_b rows / my coarse_x window (alias the full vectors on rank 0)
   bool own_cb = false, own_cx = false;
   double* xfull = nullptr;       // staging for the final all-gather when the caller's x is host memory
+  // The level below may be partitioned too (B200AMG_OPT_PART_LEVELS): then cb / cx ARE the child's b / x
+  // ([owned | halo]) and P's columns are the child's local ids.  P is therefore uploaded only when the next
+  // add_level / set_coarse call tells what the level below looks like.
+  int level = 0;
+  Part* child = nullptr;
+  HostCsr pendP;
+  bool pendingP = false;
   const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
   void release() {
     A.release(); At.release(); R.release(); P.release();
@@ -639,7 +646,9 @@ struct b200amg_hierarchy {
   int rank = 0, world = 1;
   ncclUniqueId nccl_id;
   ncclComm_t comm = nullptr;
-  std::unique_ptr<Part> part;
+  std::vector<std::unique_ptr<Part>> parts;   // partitioned levels 0 .. parts.size()-1
+  Part* part = nullptr;                       // parts[0]: what solve / cycle / precond load and store
+  int part_levels = 1;                        // how many of the finest levels are partitioned (world > 1)
   cudaStream_t stream = nullptr;
   std::vector<std::unique_ptr<Level>> levels;
   // coarsest
@@ -1222,8 +1231,7 @@ __global__ void __launch_bounds__(kThreads) halo_pack_kernel(int n, const int* _
 }
 
 // v is laid out [owned | halo]: gather what the neighbours need, exchange, receive straight into the halo
-static void halo_exchange(H* h, double* v) {
-  Part& P = *h->part;
+static void halo_exchange(H* h, Part& P, double* v) {
   const PartPlan& pl = P.plan;
   NcclApi& nc = nccl_api();
   const int nsend = pl.send_off[pl.world];
@@ -1242,16 +1250,15 @@ static void halo_exchange(H* h, double* v) {
   h->collectives++;
 }
 
-static void smooth_part(H* h, const SmootherCfg& c) {
-  Part& P = *h->part;
+static void smooth_part(H* h, Part& P, const SmootherCfg& c) {
   if (c.kind == B200AMG_SMOOTHER_NONE || P.plan.nloc == 0) {
-    if (c.kind != B200AMG_SMOOTHER_NONE) for (int it = 0; it < c.iter; ++it) halo_exchange(h, P.x);   // keep the collectives matched
+    if (c.kind != B200AMG_SMOOTHER_NONE) for (int it = 0; it < c.iter; ++it) halo_exchange(h, P, P.x);   // keep the collectives matched
     return;
   }
   double* cur = P.x;
   double* other = P.temp;
   for (int it = 0; it < c.iter; ++it) {
-    halo_exchange(h, cur);
+    halo_exchange(h, P, cur);
     if (P.symmetry == B200AMG_SYMMETRY_NONE) launch_jacobi_general(h, P.A, P.diag, cur, P.b, other, c.omega);
     else launch_jacobi_fast(h, P.walked(), cur, P.b, other, c.omega);
     std::swap(cur, other);
@@ -1262,17 +1269,35 @@ static void smooth_part(H* h, const SmootherCfg& c) {
 static void solve_level(H* h, double* x, int cycle, const double* b, int lvl, bool x_is_zero);
 static void coarse_solve(H* h, double* x, const double* b);
 
-// __solve!(x, ml, cycle, b, 1) with level 1 split by rows (multilevel.jl:214-239)
-static void cycle_body_part(H* h, int cycle) {
-  Part& P = *h->part;
+// __solve!(x, ml, cycle, b, lvl) for a level split by rows (multilevel.jl:214-239)
+static void cycle_part_level(H* h, int lvl, int cycle) {
+  Part& P = *h->parts[lvl];
   const PartPlan& pl = P.plan;
   NcclApi& nc = nccl_api();
-  Level& L0 = *h->levels[0];
-  smooth_part(h, P.pre);                                                         // :216
-  halo_exchange(h, P.x);
+  Level& L0 = *h->levels[lvl];
+  smooth_part(h, P, P.pre);                                                      // :216
+  halo_exchange(h, P, P.x);
   residual(h, P.A, P.x, P.b, P.res);                                            // :219-220
-  halo_exchange(h, P.res);
+  halo_exchange(h, P, P.res);
   spmv(h, P.R, P.res, P.cb);                                                     // :223 (my coarse rows)
+  if (P.child) {
+    // the level below is partitioned too: the restriction wrote straight into its b (the rows I own there)
+    Part& C = *P.child;
+    CUDA_OK(cudaMemsetAsync(C.x, 0, sizeof(double) * (size_t)std::max<int64_t>(C.plan.nloc, 1), h->stream));   // :226
+    if (cycle == B200AMG_CYCLE_V) {
+      cycle_part_level(h, lvl + 1, B200AMG_CYCLE_V);
+    } else if (cycle == B200AMG_CYCLE_W) {
+      cycle_part_level(h, lvl + 1, B200AMG_CYCLE_W);
+      cycle_part_level(h, lvl + 1, B200AMG_CYCLE_W);
+    } else {
+      cycle_part_level(h, lvl + 1, B200AMG_CYCLE_F);
+      cycle_part_level(h, lvl + 1, B200AMG_CYCLE_V);
+    }
+    halo_exchange(h, C, C.x);                                                    // my rows of P reach into the neighbours' coarse entries
+    spmv_add(h, P.P, C.x, P.x);                                                  // :233-234
+    smooth_part(h, P, P.post);                                                   // :236
+    return;
+  }
   NCCL_OK(nc.GroupStart());                                                      // coarse_b -> rank 0
   if (pl.rank == 0) {
     for (int q = 1; q < pl.world; ++q) {
@@ -1288,16 +1313,16 @@ static void cycle_body_part(H* h, int cycle) {
     // everything below the partitioned level is a static kernel sequence on this rank: one graph per cycle type
     auto coarse_part = [&]() {
       CUDA_OK(cudaMemsetAsync(L0.coarse_x, 0, sizeof(double) * (size_t)std::max<int64_t>(L0.nc, 1), h->stream));   // :226
-      if (h->levels.size() == 1) {
+      if ((int)h->levels.size() == lvl + 1) {
         coarse_solve(h, L0.coarse_x, L0.coarse_b);                                  // :228
       } else if (cycle == B200AMG_CYCLE_V) {
-        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, true);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, lvl + 1, true);
       } else if (cycle == B200AMG_CYCLE_W) {
-        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, true);
-        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, 1, false);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, lvl + 1, true);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_W, L0.coarse_b, lvl + 1, false);
       } else {
-        solve_level(h, L0.coarse_x, B200AMG_CYCLE_F, L0.coarse_b, 1, true);
-        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, 1, false);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_F, L0.coarse_b, lvl + 1, true);
+        solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, lvl + 1, false);
       }
     };
     if (h->part_graphs && !h->cycle_graph[cycle] && h->cycle_graph_launches[cycle] >= 0 && !h->profiling) {
@@ -1338,8 +1363,9 @@ static void cycle_body_part(H* h, int cycle) {
   NCCL_OK(nc.GroupEnd());
   h->collectives++;
   spmv_add(h, P.P, P.cx, P.x);                                                   // :233-234
-  smooth_part(h, P.post);                                                        // :236
+  smooth_part(h, P, P.post);                                                     // :236
 }
+static void cycle_body_part(H* h, int cycle) { cycle_part_level(h, 0, cycle); }
 
 // sum over ranks of a device scalar, in place; every rank gets the same bits
 static void allreduce_scalar(H* h, double* dev) {
@@ -1356,7 +1382,7 @@ static void sumsq_part(H* h, const double* v, double* out_dev) {
 }
 static void residual_norm_part(H* h) {   // scalars[0] = ||b - A x||^2 over all ranks
   Part& P = *h->part;
-  halo_exchange(h, P.x);
+  halo_exchange(h, P, P.x);
   const bool timed = h->time_residual && h->res_events_used + 2 <= (int)h->res_events.size();
   if (timed) CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used], h->stream));
   residual(h, P.A, P.x, P.b, P.res);
@@ -1532,24 +1558,30 @@ static void finish_transfer_operators(Level& prev, const HostPerm* coarse) {
   prev.pending = false;
 }
 
-// level 1 of a partitioned hierarchy: local blocks, halo plan, local vectors
-static void build_part(H* h, Level& L, const HostCsr& hAt, const HostCsr& hP, const HostCsr& hR, int symmetry) {
+// One partitioned level: local blocks of A, A', R, the halo plan and the local vectors.  P waits (pendP) until the
+// next add_level / set_coarse call says whether the level below is partitioned as well.
+static void build_part_level(H* h, Level& L, const HostCsr& hAt, HostCsr& hP, const HostCsr& hR, int symmetry) {
   std::unique_ptr<Part> part(new Part());
   Part& P = *part;
+  P.level = (int)h->parts.size();
   P.n = L.n; P.nc = L.nc; P.symmetry = symmetry; P.pre = L.pre; P.post = L.post;
   auto ok = [](const SmootherCfg& c) { return c.kind == B200AMG_SMOOTHER_NONE || c.kind == B200AMG_SMOOTHER_JACOBI; };
   REQUIRE(ok(L.pre) && ok(L.post), B200AMG_ERR_UNSUPPORTED,
-          "Gauss-Seidel / SOR do not shard (the sweep is sequential over the whole index range): use Jacobi on a partitioned fine level");
+          "Gauss-Seidel / SOR do not shard (the sweep is sequential over the whole index range): use Jacobi on a partitioned level");
   HostCsr hA = transpose(hAt);
   const bool sym = bit_equal(hA, hAt);
-  P.plan = make_part_plan(h->rank, h->world, hA, sym ? nullptr : &hAt, hR, hP);
+  Part* parent = P.level > 0 ? h->parts[P.level - 1].get() : nullptr;
+  if (parent)
+    P.plan = make_part_plan(h->rank, h->world, hA, sym ? nullptr : &hAt, hR, hP, &parent->plan.coarse_split, &parent->pendP,
+                            &parent->plan.row_split);
+  else
+    P.plan = make_part_plan(h->rank, h->world, hA, sym ? nullptr : &hAt, hR, hP);
   const PartPlan& pl = P.plan;
   const int64_t lo = pl.row_split[pl.rank], hi = pl.row_split[pl.rank + 1];
   P.A.upload(part_local_block(hA, lo, hi, lo, hi, pl.halo_cols));
   if (sym) P.At.alias(P.A);
   else P.At.upload(part_local_block(hAt, lo, hi, lo, hi, pl.halo_cols));
   P.R.upload(part_local_block(hR, pl.coarse_split[pl.rank], pl.coarse_split[pl.rank + 1], lo, hi, pl.halo_cols));
-  P.P.upload(part_shifted_block(hP, lo, hi, pl.cx_lo, pl.cx_hi - pl.cx_lo));
   {
     const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt : hA;
     std::vector<double> d((size_t)pl.nloc, 0.0);
@@ -1563,14 +1595,38 @@ static void build_part(H* h, Level& L, const HostCsr& hAt, const HostCsr& hP, co
   const int64_t nv = pl.nloc + pl.nhalo + 8;
   P.x = dev_alloc<double>(nv); P.b = dev_alloc<double>(nv); P.res = dev_alloc<double>(nv); P.temp = dev_alloc<double>(nv);
   for (double* v : {P.x, P.b, P.res, P.temp}) CUDA_OK(cudaMemset(v, 0, sizeof(double) * (size_t)nv));
+  P.pendP = std::move(hP);
+  P.pendingP = true;
+  if (parent) {   // the parent restricts into my b and prolongs from my x ([owned | halo] ids)
+    const PartPlan& pp = parent->plan;
+    parent->child = &P;
+    parent->cb = P.b;
+    parent->cx = P.x;
+    parent->P.upload(part_local_block(parent->pendP, pp.row_split[pp.rank], pp.row_split[pp.rank + 1], lo, hi, pl.halo_cols));
+    parent->pendP = HostCsr();
+    parent->pendingP = false;
+  }
+  h->parts.push_back(std::move(part));
+  h->part = h->parts[0].get();
+}
+// the level below the LAST partitioned level lives on rank 0: coarse_b slices are gathered there, coarse_x windows sent back
+static void finish_last_part_level(H* h) {
+  if (h->parts.empty() || !h->parts.back()->pendingP) return;
+  Part& P = *h->parts.back();
+  Level& L = *h->levels[P.level];
+  const PartPlan& pl = P.plan;
   if (pl.rank == 0) {   // my coarse rows / window are slices of the full vectors
+    L.coarse_x = dev_alloc<double>(L.nc + 8);
+    L.coarse_b = dev_alloc<double>(L.nc + 8);
     P.cb = L.coarse_b + pl.coarse_split[0];
     P.cx = L.coarse_x + pl.cx_lo;
   } else {
     P.cb = dev_alloc<double>(pl.ncloc + 8); P.own_cb = true;
     P.cx = dev_alloc<double>(pl.cx_hi - pl.cx_lo + 8); P.own_cx = true;
   }
-  h->part = std::move(part);
+  P.P.upload(part_shifted_block(P.pendP, pl.row_split[pl.rank], pl.row_split[pl.rank + 1], pl.cx_lo, pl.cx_hi - pl.cx_lo));
+  P.pendP = HostCsr();
+  P.pendingP = false;
 }
 
 int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R,
@@ -1588,8 +1644,9 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
   if (!h->levels.empty())
     REQUIRE(h->levels.back()->nc == L->n, B200AMG_ERR_DIM_MISMATCH, "level has %lld rows but the previous level coarsens to %lld",
             (long long)L->n, (long long)h->levels.back()->nc);
-  const bool fine_of_partition = h->world > 1 && h->levels.empty();
-  const bool remote = h->world > 1 && !h->levels.empty() && h->rank != 0;   // coarse levels live on rank 0 only
+  const bool fine_of_partition = h->world > 1 && (int)h->levels.size() < h->part_levels;   // this level is split by rows
+  if (h->world > 1 && !fine_of_partition) finish_last_part_level(h);
+  const bool remote = h->world > 1 && !fine_of_partition && h->rank != 0;   // the other levels live on rank 0 only
   {
     HostCsr hP = stage_operator_by_rows(P);
     HostCsr hR = stage_operator_by_rows(R);
@@ -1602,17 +1659,13 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
     HostCsr hAt = stage_csc_as_rows_of_transpose(A);
     L->nnz_a = hAt.nnz();
     if (fine_of_partition) {
-      if (h->rank == 0) {
-        L->coarse_x = dev_alloc<double>(L->nc + 8);
-        L->coarse_b = dev_alloc<double>(L->nc + 8);
-      }
       L->remote = true;   // no full device copy of this level on any rank
-      build_part(h, *L, hAt, hP, hR, symmetry);
+      build_part_level(h, *L, hAt, hP, hR, symmetry);
     } else if (remote) {
       L->remote = true;
     } else {
       L->M.build(hAt, symmetry, cfg_needs_fwd(L->pre) || cfg_needs_fwd(L->post), cfg_needs_bwd(L->pre) || cfg_needs_bwd(L->post), true);
-      REQUIRE(!(h->part && h->levels.size() == 1 && !L->M.perm.identity()), B200AMG_ERR_UNSUPPORTED,
+      REQUIRE(!(h->part && h->levels.size() == h->parts.size() && !L->M.perm.identity()), B200AMG_ERR_UNSUPPORTED,
               "the level below a partitioned fine level must use Jacobi smoothing (its numbering is shared with the other ranks)");
       // this level's numbering: rows of P, columns of R now; the coarse side when the next level arrives
       L->pendP = permute_rows(hP, L->M.perm);
@@ -1644,6 +1697,7 @@ int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int
   set_device(h);
   REQUIRE(h->world == 1 || !h->levels.empty(), B200AMG_ERR_UNSUPPORTED, "a partitioned hierarchy needs at least one level");
   if (!h->levels.empty()) finish_transfer_operators(*h->levels.back(), nullptr);   // the coarsest level keeps its numbering
+  if (h->world > 1) finish_last_part_level(h);
   h->nfinal = n;
   if (h->world == 1 || h->rank == 0) {
     HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
@@ -1668,6 +1722,7 @@ int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_si
   }
   h->rank = rank;
   h->world = world_size;
+  h->part_levels = std::max(1, env_int("B200AMG_PART_LEVELS", h->part_levels));
   API_END
 }
 
@@ -1754,7 +1809,7 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
     L->M.release(); L->P.release(); L->R.release();
     cudaFree(L->res); cudaFree(L->temp); cudaFree(L->coarse_x); cudaFree(L->coarse_b);
   }
-  if (h->part) h->part->release();
+  for (auto& pp : h->parts) pp->release();
   if (h->comm) nccl_api().CommDestroy(h->comm);
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
@@ -2128,11 +2183,11 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
       switch (what) {
         case 0: spmv(h, P.A, P.x, P.res); break;
         case 1: residual(h, P.A, P.x, P.b, P.res); break;
-        case 2: smooth_part(h, P.pre); break;
+        case 2: smooth_part(h, P, P.pre); break;
         case 3: spmv(h, P.R, P.res, P.cb); break;
         case 4: spmv_add(h, P.P, P.cx, P.x); break;
         case 6: sumsq_part(h, P.b, h->scalars + 4); break;
-        case 7: halo_exchange(h, P.x); break;
+        case 7: halo_exchange(h, P, P.x); break;
         default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown kernel selector %d", what);
       }
     } else if (what == 6) {
@@ -2197,6 +2252,10 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_CTA_ROWS: h->gs_cta_rows = (int64_t)value; break;
     case B200AMG_OPT_GS_MAIL_MIN_WIDTH: h->gs_mail_min_width = (int64_t)value; break;
     case B200AMG_OPT_GS_CLUSTER: h->gs_cluster = (int)value; break;
+    case B200AMG_OPT_PART_LEVELS:
+      REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
+      h->part_levels = std::max(1, (int)value);
+      break;
     case 10: h->gs_cluster_log_nc = (int)value; break;     // experiment knobs (tools/tune_kernels.py)
     case 11: h->gs_cluster_threads = (int)value; break;
     case B200AMG_OPT_GS_GATE_SLEEP: h->gs_gate_sleep = (int)value; break;

@@ -57,16 +57,23 @@ inline void part_sort_unique(std::vector<int>& v) {
 }
 
 // A, At: n x n by rows (At may alias A); R: nc x n by rows; P: n x nc by rows.
+// given_split: row blocks to use (a level below a partitioned one inherits its parent's coarse_split) or nullptr.
+// parentP / parent_split: the prolongation of the level above and its row blocks — the entries of THIS level's x that
+// the parent's owned rows of P reference must be in the halo too (nullptr for the finest level).
 template <class Csr>
-PartPlan make_part_plan(int rank, int world, const Csr& A, const Csr* At, const Csr& R, const Csr& P) {
+PartPlan make_part_plan(int rank, int world, const Csr& A, const Csr* At, const Csr& R, const Csr& P,
+                        const std::vector<int64_t>* given_split = nullptr, const Csr* parentP = nullptr,
+                        const std::vector<int64_t>* parent_split = nullptr) {
   PartPlan pl;
   pl.rank = rank;
   pl.world = world;
   const int64_t n = A.nrows, nc = R.nrows;
-  // ---- row blocks balanced by nnz(A) ----
+  // ---- row blocks: inherited, or balanced by nnz(A) ----
   pl.row_split.assign(world + 1, n);
   pl.row_split[0] = 0;
-  {
+  if (given_split) {
+    pl.row_split = *given_split;
+  } else {
     const double total = (double)A.ptr[n];
     int64_t r = 0;
     for (int g = 1; g < world; ++g) {
@@ -93,6 +100,8 @@ PartPlan make_part_plan(int rank, int world, const Csr& A, const Csr* At, const 
     part_collect_external(A.ptr.data(), A.idx.data(), lo, hi, lo, hi, hcols);
     if (At && At != &A) part_collect_external(At->ptr.data(), At->idx.data(), lo, hi, lo, hi, hcols);
     part_collect_external(R.ptr.data(), R.idx.data(), pl.coarse_split[g], pl.coarse_split[g + 1], lo, hi, hcols);
+    if (parentP && parent_split)
+      part_collect_external(parentP->ptr.data(), parentP->idx.data(), (*parent_split)[g], (*parent_split)[g + 1], lo, hi, hcols);
     part_sort_unique(hcols);
   }
   const int64_t lo = pl.row_split[rank], hi = pl.row_split[rank + 1];

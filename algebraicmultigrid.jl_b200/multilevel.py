@@ -76,11 +76,12 @@ class MultiLevel:
             self._dev = _devlib.DeviceHierarchy(self, partition=self._partition)
         return self._dev
 
-    def partition(self, rank, world_size, nccl_unique_id):
-        """Make this process one rank of a row-partitioned fine level (call before first use)."""
+    def partition(self, rank, world_size, nccl_unique_id, levels=1):
+        """Make this process one rank of a hierarchy whose ``levels`` finest levels are split by rows over
+        ``world_size`` GPUs (call before first use); the remaining levels live on rank 0."""
         if self._dev is not None:
             raise RuntimeError("partition() must be called before the hierarchy is uploaded")
-        self._partition = (rank, world_size, nccl_unique_id)
+        self._partition = (rank, world_size, nccl_unique_id, int(levels))
 
     def release(self):
         if self._dev is not None:

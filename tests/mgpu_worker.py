@@ -20,14 +20,15 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     jac = amg.Jacobi(2.0 / 3.0)
     failures = []
-    cases = [("rs", (40, 40, 40)), ("sa", (96, 96)), ("rs", (1000,))]
-    for method, dims in cases:
+    cases = [("rs", (40, 40, 40), 1), ("rs", (40, 40, 40), 2), ("rs", (40, 40, 40), 3), ("sa", (96, 96), 1), ("sa", (96, 96), 2),
+             ("rs", (1000,), 1), ("rs", (1000,), 4)]
+    for method, dims, plevels in cases:
         A = amg.poisson(dims if len(dims) > 1 else dims[0])
         build = amg.ruge_stuben if method == "rs" else amg.smoothed_aggregation
         ml = build(A, presmoother=jac, postsmoother=jac)
         box = [_devlib.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        ml.partition(rank, world, box[0])
+        ml.partition(rank, world, box[0], levels=plevels)
         b = np.random.default_rng(3).random(A.n)
         H = oracle.OracleHierarchy(build(A, presmoother=jac, postsmoother=jac)) if rank == 0 else None
         for cyc, cname in ((amg.V(), "V"), (amg.W(), "W"), (amg.F(), "F")):
@@ -45,10 +46,10 @@ def main():
                 e = np.linalg.norm(x - xr) / np.linalg.norm(xr)
                 ep = np.abs(p - H.precond(b, cycle=cname)).max() / np.abs(r1).max()
                 ok = e1 < 1e-11 and e < 1e-9 and ep < 1e-11 and len(hist) == len(histr) and np.allclose(hist, histr, rtol=1e-6) and same
-                print(f"[mgpu] {method} {dims} {cname}: cycle {e1:.1e} solve {e:.1e} precond {ep:.1e} iters {len(hist) - 1}/{len(histr) - 1} "
+                print(f"[mgpu] {method} {dims} part_levels={plevels} {cname}: cycle {e1:.1e} solve {e:.1e} precond {ep:.1e} iters {len(hist) - 1}/{len(histr) - 1} "
                       f"same_on_all_ranks={same} {'OK' if ok else 'FAIL'}", flush=True)
                 if not ok:
-                    failures.append((method, dims, cname))
+                    failures.append((method, dims, plevels, cname))
             elif not same:
                 failures.append(("rank", rank))
         if rank == 0:
