@@ -23,6 +23,7 @@
 #include "stream.cuh"
 #include "partition.h"
 #include "cluster_gs.cuh"
+#include "dsm_gs.cuh"
 
 using namespace b200amg;
 
@@ -485,6 +486,12 @@ struct SmootherMatrix {
   int* d_fwd_lvlptr = nullptr;   // forward wavefront boundaries (single-CTA sweep)
   int nlev = 0;
   bool pattern_symmetric = false;
+  // one-cluster sweep with x in distributed shared memory (dsm_gs.cuh): wavefront-aligned tiles of <= 256/T rows
+  int4* dsm_meta = nullptr;
+  int2* dsm_aux = nullptr;
+  int *dsm_code = nullptr, *dsm_rowof = nullptr, *dsm_own_off = nullptr, *dsm_wave_tiles = nullptr;
+  int dsm_ntiles = 0, dsm_lanes = 0, dsm_log_nc = 0, dsm_slots_max = 0;
+  int* dsm_status = nullptr;
   uint4* mail = nullptr;
   unsigned* mail_ctl = nullptr;
   const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
@@ -548,6 +555,85 @@ struct SmootherMatrix {
       d_fwd_lvlptr = dev_upload(lvlptr, 8);
       nlev = (int)lvlptr.size() - 1;
     }
+    if ((need_fwd || need_bwd) && n > 0 && n <= (int64_t)16 * 28000 && mean >= 6.0 && lvlptr.size() >= 2) {
+      // plan of the distributed-shared-memory sweep (dsm_gs.cuh): tiles never cross a wavefront, <= 256/T rows,
+      // <= kDsmTileNnz entries; tile t belongs to CTA t % NC, which also keeps the x of the tile's rows
+      int T = 4;
+      while (T < 32 && kDsmBurst * T < 1.6 * mean) T *= 2;   // one gather burst covers all but the longest rows
+      T = std::min(32, std::max(4, env_int("B200AMG_DSM_LANES", T)));
+      const int G = kDsmThreads / T;
+      std::vector<int4> tm;
+      std::vector<int2> ta;
+      bool ok = true;
+      const int nl = (int)lvlptr.size() - 1;
+      std::vector<int> wave_tiles((size_t)nl, 0);
+      for (int wv = 0; wv < nl && ok; ++wv) {
+        int r = lvlptr[wv];
+        while (r < lvlptr[wv + 1]) {
+          int e2 = r;
+          const int k0 = w.ptr[r];
+          while (e2 < lvlptr[wv + 1] && e2 - r < G && w.ptr[e2 + 1] - k0 <= kDsmTileNnz) ++e2;
+          if (e2 == r) { ok = false; break; }   // a row longer than a tile
+          tm.push_back(make_int4(r, e2, k0, w.ptr[e2]));
+          ta.push_back(make_int2(wv, 0));
+          ++wave_tiles[wv];
+          r = e2;
+        }
+      }
+      if (ok) {
+        auto slots_max_for = [&](int lnc) {
+          std::vector<int64_t> cnt((size_t)1 << lnc, 0);
+          for (size_t t = 0; t < tm.size(); ++t) cnt[t & ((1u << lnc) - 1)] += tm[t].y - tm[t].x;
+          return *std::max_element(cnt.begin(), cnt.end());
+        };
+        int lnc = 0;
+        while (lnc <= 4 && dsm_smem_bytes(slots_max_for(lnc), nl) > (size_t)kDsmMaxDynSmem) ++lnc;
+        const int lnc_fit = lnc;
+        const int lnc_max = std::min(4, std::max(0, env_int("B200AMG_GS_DSM_MAX_LOG_NC", 4)));
+        const double wave_rows = (double)n / (double)nl;
+        while (lnc < lnc_max && wave_rows > (double)G * (double)(1 << lnc)) ++lnc;   // one pass of all CTAs covers a mean wavefront
+        const int forced = env_int("B200AMG_GS_DSM_LOG_NC", -1);
+        if (forced >= 0) lnc = std::min(4, std::max(lnc_fit, forced));
+        if (lnc <= 4) {
+          const int NC = 1 << lnc;
+          std::vector<int> running(NC, 0), code_of_row((size_t)n, 0);
+          std::vector<std::vector<int>> rows_of(NC);
+          for (size_t t = 0; t < tm.size(); ++t) {
+            const int owner = (int)(t & (size_t)(NC - 1));
+            ta[t].y = running[owner];
+            for (int r = tm[t].x; r < tm[t].y; ++r) {
+              code_of_row[r] = (running[owner] << lnc) | owner;
+              rows_of[owner].push_back(r);
+              ++running[owner];
+            }
+          }
+          std::vector<int> own_off(NC + 2, 0), rowof;
+          rowof.reserve((size_t)n);
+          for (int c = 0; c < NC; ++c) {
+            own_off[c + 1] = own_off[c] + running[c];
+            rowof.insert(rowof.end(), rows_of[c].begin(), rows_of[c].end());
+          }
+          own_off[NC + 1] = *std::max_element(running.begin(), running.end());
+          std::vector<int> code(w.idx.size());
+          for (size_t k = 0; k < w.idx.size(); ++k) code[k] = code_of_row[w.idx[k]];
+          dsm_meta = dev_upload(tm);
+          dsm_aux = dev_upload(ta);
+          dsm_code = dev_upload(code, 8);
+          dsm_rowof = dev_upload(rowof, 8);
+          dsm_own_off = dev_upload(own_off);
+          dsm_wave_tiles = dev_upload(wave_tiles);
+          dsm_ntiles = (int)tm.size();
+          dsm_lanes = T;
+          dsm_log_nc = lnc;
+          dsm_slots_max = own_off[NC + 1];
+          dsm_status = dev_alloc<int>(4);
+          CUDA_OK(cudaMemset(dsm_status, 0, 4 * sizeof(int)));
+          if (env_int("B200AMG_GS_DSM_VERBOSE", 0))
+            fprintf(stderr, "[b200amg] dsm plan: n=%lld nnz=%lld wavefronts=%d lanes=%d ctas=%d tiles=%d slots/cta=%d smem=%zu\n",
+                    (long long)n, (long long)w.nnz(), nl, T, NC, dsm_ntiles, dsm_slots_max, dsm_smem_bytes(dsm_slots_max, nl));
+        }
+      }
+    }
     if ((need_fwd || need_bwd) && pattern_symmetric && n > 0) {
       gs_lanes = 1;
       while (gs_lanes < 32 && kGsPrefetch * gs_lanes < (mean <= kGsPrefetch ? mean : 1.25 * mean)) gs_lanes *= 2;
@@ -584,6 +670,8 @@ struct SmootherMatrix {
   void release() {
     A.release(); At.release(); fwd.release(); bwd.release();
     cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr); cudaFree(gs_meta); cudaFree(gs_tile_wave);
+    cudaFree(dsm_meta); cudaFree(dsm_aux); cudaFree(dsm_status); cudaFree(dsm_code); cudaFree(dsm_rowof); cudaFree(dsm_own_off); cudaFree(dsm_wave_tiles);
+    dsm_meta = nullptr; dsm_aux = nullptr; dsm_status = nullptr; dsm_code = dsm_rowof = dsm_own_off = dsm_wave_tiles = nullptr; dsm_ntiles = 0;
     d_fwd_lvlptr = nullptr; gs_meta = nullptr; gs_tile_wave = nullptr; gs_ntiles = 0;
     diag = nullptr; d_new_of_old = d_old_of_new = nullptr; mail = nullptr; mail_ctl = nullptr;
   }
@@ -678,6 +766,9 @@ struct b200amg_hierarchy {
                                       // 2.4-3.9 us per wavefront vs 2.2-2.5 for the counter sweep, so off by default
   int64_t gs_cluster_rows = 380000;
   int gs_cluster_log_nc = 3, gs_cluster_threads = 256;
+  int gs_dsm = 0;                     // 1: one-cluster sweep with x in distributed shared memory + per-wavefront arrival
+                                      // counters in shared memory (dsm_gs.cuh) on every level it fits
+  int gs_dsm_fence = 0;               // bit 0 / 1: cluster-scope fence on the producer / consumer side of the hand-off
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
@@ -979,6 +1070,87 @@ static bool launch_gs_cluster(H* h, const SmootherMatrix& M, const DevCsr& A, co
 #undef B200AMG_CL
   return launch_gs_cluster_T<4, 1024>(h, M, A, sc, x, b, w, sor);
 }
+// attributes + schedulability of one instantiation, probed once (at b200amg_create: never inside a stream capture)
+template <int LOG_NC, int T>
+static int dsm_state() {
+  static int state = 0;   // 1 usable, -1 not schedulable on this device
+  if (state != 0) return state;
+  constexpr int NC = 1 << LOG_NC;
+  cudaLaunchConfig_t probe = {};
+  probe.gridDim = dim3(NC, 1, 1);
+  probe.blockDim = dim3(kDsmBlock, 1, 1);
+  probe.dynamicSmemBytes = kDsmMaxDynSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  probe.attrs = attr;
+  probe.numAttrs = NC > 1 ? 1 : 0;
+  int nclusters = 1;
+  if (cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsmMaxDynSmem) != cudaSuccess ||
+      (NC > 8 && cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+      (NC > 1 && (cudaOccupancyMaxActiveClusters(&nclusters, gs_dsm_kernel<LOG_NC, T>, &probe) != cudaSuccess || nclusters < 1))) {
+    cudaGetLastError();
+    state = -1;
+  } else {
+    state = 1;
+  }
+  return state;
+}
+template <int LOG_NC>
+static void dsm_init_nc() { dsm_state<LOG_NC, 4>(); dsm_state<LOG_NC, 8>(); dsm_state<LOG_NC, 16>(); dsm_state<LOG_NC, 32>(); }
+static void dsm_kernels_init() { dsm_init_nc<0>(); dsm_init_nc<1>(); dsm_init_nc<2>(); dsm_init_nc<3>(); dsm_init_nc<4>(); }
+// ---- one-cluster sweep, x in distributed shared memory, dataflow hand-off through shared memory (dsm_gs.cuh) ----
+template <int LOG_NC, int T>
+static bool launch_gs_dsm_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                            int sor) {
+  constexpr int NC = 1 << LOG_NC;
+  const size_t smem = dsm_smem_bytes(M.dsm_slots_max, M.nlev);
+  if (dsm_state<LOG_NC, T>() < 0 || smem > (size_t)kDsmMaxDynSmem) return false;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NC, 1, 1);
+  cfg.blockDim = dim3(kDsmBlock, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = NC > 1 ? 1 : 0;
+  CUDA_OK(cudaLaunchKernelEx(&cfg, gs_dsm_kernel<LOG_NC, T>, (int)M.n, M.dsm_ntiles, M.nlev, (const int4*)M.dsm_meta,
+                             (const int2*)M.dsm_aux, (const int*)A.ptr, (const int*)M.dsm_code, (const double*)A.val,
+                             (const int*)M.dsm_rowof, (const int*)M.dsm_own_off, (const int*)M.dsm_wave_tiles, x, b, w, sor,
+                             sc.backward, h->opaque_zero,
+                             h->gs_dsm_fence, M.dsm_status, h->gs_debug));
+  count_launch(h);
+  return true;
+}
+template <int LOG_NC>
+static bool launch_gs_dsm_NC(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b,
+                             double w, int sor) {
+  switch (M.dsm_lanes) {
+    case 4: return launch_gs_dsm_T<LOG_NC, 4>(h, M, A, sc, x, b, w, sor);
+    case 8: return launch_gs_dsm_T<LOG_NC, 8>(h, M, A, sc, x, b, w, sor);
+    case 16: return launch_gs_dsm_T<LOG_NC, 16>(h, M, A, sc, x, b, w, sor);
+    case 32: return launch_gs_dsm_T<LOG_NC, 32>(h, M, A, sc, x, b, w, sor);
+    default: return false;
+  }
+}
+static bool launch_gs_dsm(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                          int sor) {
+  if (M.dsm_ntiles <= 0 || M.dsm_lanes < 4 || M.nlev <= 0 || !M.dsm_code) return false;
+  switch (M.dsm_log_nc) {
+    case 0: return launch_gs_dsm_NC<0>(h, M, A, sc, x, b, w, sor);
+    case 1: return launch_gs_dsm_NC<1>(h, M, A, sc, x, b, w, sor);
+    case 2: return launch_gs_dsm_NC<2>(h, M, A, sc, x, b, w, sor);
+    case 3: return launch_gs_dsm_NC<3>(h, M, A, sc, x, b, w, sor);
+    case 4: return launch_gs_dsm_NC<4>(h, M, A, sc, x, b, w, sor);
+    default: return false;
+  }
+}
 constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
 template <int T, bool XS>
 static void gs_cta_set_attr() {
@@ -1020,6 +1192,11 @@ static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const 
 }
 static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   const DevCsr& A = M.walked();
+  if (h->gs_mode >= 1 && h->gs_dsm && M.d_fwd_lvlptr && !(sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width)) {
+    if (launch_gs_dsm(h, M, A, sc, x, b, w, sor)) return;
+    REQUIRE(h->gs_dsm < 2 || M.dsm_ntiles <= 0, B200AMG_ERR_CUDA, "the distributed-shared-memory sweep could not be launched (n = %lld, %d CTAs)",
+            (long long)M.n, 1 << M.dsm_log_nc);
+  }
   // Which sweep: measured on B200 (tools/tune_kernels.py, profiles/): one CTA wins while x fits in shared
   // memory (~1 us per wavefront); the per-row mailbox sweep wins on wide wavefronts (>= ~1000 rows); the
   // wavefront-counter sweep in between.
@@ -1525,6 +1702,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   stream_kernels_init();
   gs_cta_kernels_init();
+  dsm_kernels_init();
   gs_tile_ctas<1>(); gs_tile_ctas<2>(); gs_tile_ctas<4>(); gs_tile_ctas<8>(); gs_tile_ctas<16>(); gs_tile_ctas<32>();
   h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
   h->gs_mode = env_int("B200AMG_GS_MODE", 2);
@@ -1534,6 +1712,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 1);
   h->gs_counter_mail = env_int("B200AMG_GS_COUNTER_MAIL", 1);
   h->gs_cluster = env_int("B200AMG_GS_CLUSTER", 0);
+  h->gs_dsm = env_int("B200AMG_GS_DSM", 0);
+  h->gs_dsm_fence = env_int("B200AMG_GS_DSM_FENCE", 0);
   h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
@@ -2252,6 +2432,8 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_CTA_ROWS: h->gs_cta_rows = (int64_t)value; break;
     case B200AMG_OPT_GS_MAIL_MIN_WIDTH: h->gs_mail_min_width = (int64_t)value; break;
     case B200AMG_OPT_GS_CLUSTER: h->gs_cluster = (int)value; break;
+    case B200AMG_OPT_GS_DSM: h->gs_dsm = (int)value; break;
+    case B200AMG_OPT_GS_DSM_FENCE: h->gs_dsm_fence = (int)value; break;
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
       h->part_levels = std::max(1, (int)value);
@@ -2288,7 +2470,8 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   Level& L = *h->levels[level];
   const DevSchedule& sc = backward ? L.M.bwd : L.M.fwd;
   REQUIRE(sc.built, B200AMG_ERR_STATE, "no Gauss-Seidel schedule on this level");
-  const int64_t words = (int64_t)sc.ntasks * 8;
+  const bool dsm = h->gs_dsm && L.M.dsm_ntiles > 0;   // stamps of the distributed-shared-memory sweep: 8 per tile (dsm_gs.cuh)
+  const int64_t words = (int64_t)(dsm ? L.M.dsm_ntiles : sc.ntasks) * 8;
   REQUIRE(cap >= words, B200AMG_ERR_BAD_ARG, "timeline buffer too small (%lld needed)", (long long)words);
   unsigned long long* d = dev_alloc<unsigned long long>(words);
   CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)words, h->stream));
@@ -2296,12 +2479,13 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   const int sor = L.pre.kind == B200AMG_SMOOTHER_SOR;
   double* x = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
   const double* b = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
-  launch_dataflow(h, L.M.walked(), sc, x, b, L.pre.omega, sor);
+  if (dsm) REQUIRE(launch_gs_dsm(h, L.M, L.M.walked(), sc, x, b, L.pre.omega, sor), B200AMG_ERR_CUDA, "dsm sweep not launchable");
+  else launch_dataflow(h, L.M.walked(), sc, x, b, L.pre.omega, sor);
   h->gs_debug = nullptr;
   CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
-  *ntasks = sc.ntasks;
+  *ntasks = dsm ? L.M.dsm_ntiles : sc.ntasks;
   API_END
 }
 

@@ -139,6 +139,8 @@ def run_reference(args):
         return
     import oracle
 
+    if args.gpus > 1 and args.smoother == "gs":
+        args.smoother = "jacobi"          # same workload as our arm at N > 1 (config C4)
     amg, A, ml, b, t_setup = build_problem(args)
     H = oracle.OracleHierarchy(ml)
     budget = float(os.environ.get("B200AMG_REF_BUDGET_S", "150"))

@@ -503,3 +503,40 @@ def test_cluster_sweep_on_mid_size_level(amg):
         x = dev.smooth(lv, 0, x0.copy(), b)
         assert relinf(x, ref) <= TOL_SWEEP, (cluster, lognc, threads)
     ml.release()
+
+
+# ---- one-cluster sweep with x in distributed shared memory (csrc/device/dsm_gs.cuh) ----------------------
+@pytest.mark.parametrize("log_nc,fence", [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (2, 3), (-1, 0)])
+def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence):
+    """Every cluster size (1..16 CTAs; -1 = chosen per level) of the distributed-shared-memory sweep gives the
+    reference's sequential Gauss-Seidel / SOR sweeps (forward, backward, symmetric; Hermitian and NoSymmetry walks),
+    on stencil rows, irregular RS coarse operators and a nonsymmetric matrix; then whole cycles through it."""
+    monkeypatch.setenv("B200AMG_GS_DSM", "2")
+    monkeypatch.setenv("B200AMG_GS_DSM_FENCE", str(fence))
+    if log_nc >= 0:
+        monkeypatch.setenv("B200AMG_GS_DSM_LOG_NC", str(log_nc))
+    ml0 = amg.ruge_stuben(amg.poisson((24, 24, 24)))
+    mats = [amg.poisson((20, 17, 12)), ml0.levels[1].A, ml0.levels[2].A, fx.sprand_plus_diag(400, 0.05, 5.0, seed=11)]
+    F_, B_, S_ = amg.ForwardSweep(), amg.BackwardSweep(), amg.SymmetricSweep()
+    zoo = [amg.GaussSeidel(F_), amg.GaussSeidel(B_), amg.GaussSeidel(S_, 2), amg.SOR(0.5, F_), amg.SOR(1.3, S_, 2)]
+    r = _rng(31)
+    for A in mats:
+        x0, b = r.standard_normal(A.n), r.standard_normal(A.n)
+        for symmetry in ("hermitian", "none"):
+            sym = amg.HermitianSymmetry() if symmetry == "hermitian" else amg.NoSymmetry()
+            for sm in zoo:
+                x = x0.copy()
+                sm(A, x, b, sym)
+                ref = oracle.smooth(A, sm, x0.copy(), b, symmetry=symmetry)
+                assert relinf(x, ref) <= TOL_SWEEP, (A.n, symmetry, sm, log_nc)
+    A = amg.poisson((28, 28, 28))
+    ml = amg.ruge_stuben(A)
+    dev = ml.device()
+    launches0 = dev.launch_count()
+    b = r.random(A.n)
+    x, hist = amg._solve(ml, b, log=True)
+    xr, histr = oracle.OracleHierarchy(ml).solve(b, log=True)
+    assert len(hist) == len(histr)
+    assert np.linalg.norm(x - xr) / np.linalg.norm(xr) <= TOL_SOLVE_X
+    assert dev.launch_count() > launches0
+    ml.release()

@@ -49,7 +49,7 @@ for chunk in [int(c) for c in args.chunks.split(",")]:
             out[names[what]] = {"ms": round(ms, 4), "GBs": round(alg[what] / ms / 1e6, 1)}
         print(json.dumps(out), flush=True)
 if args.smoother == "gs":
-    for mode in (2, 3, 1):
+    for mode in [int(m) for m in os.environ.get("GS_MODES", "2,3,1").split(",")]:
         dev.set_option(3, mode)
         for lv in range(dev.nlevels - 1):
             info = dev.level_info(lv)
@@ -59,6 +59,20 @@ if args.smoother == "gs":
             print(json.dumps({"gs_mode": mode, "level": lv, "n": n, "nnz": nnz, "wavefronts": info["wavefronts"],
                               "sgs_ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1),
                               "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}), flush=True)
+if args.smoother == "gs":
+    # one-cluster sweep with x in distributed shared memory (cluster size fixed at upload: B200AMG_GS_DSM_LOG_NC)
+    dev.set_option(3, 2)
+    for fence in (0, 4, 1):
+        dev.set_option(13, 1)
+        dev.set_option(14, fence)
+        for lv in range(dev.nlevels - 1):
+            info = dev.level_info(lv)
+            n, nnz = info["n"], info["nnz_a"]
+            ms = dev.time_kernel(lv, 2, reps=5)
+            print(json.dumps({"gs_dsm": 1, "fence": fence, "log_nc_env": os.environ.get("B200AMG_GS_DSM_LOG_NC"), "level": lv, "n": n,
+                              "nnz": nnz, "wavefronts": info["wavefronts"], "sgs_ms": round(ms, 4),
+                              "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}), flush=True)
+    dev.set_option(13, 0)
 if args.smoother == "gs" and os.environ.get("SWEEP_SLEEP"):
     dev.set_option(3, 2)
     for poll, gate in ((0, 100), (0, 0), (40, 100), (0, 500), (100, 1000)):
