@@ -34,10 +34,11 @@
 namespace b200amg {
 namespace cg = cooperative_groups;
 
-constexpr int kDsmThreads = 256;          // consumer threads (relax rows); one more warp feeds the TMA ring
-constexpr int kDsmBlock = kDsmThreads + 32;
+constexpr int kDsmThreads = 256;          // consumer threads (relax rows) by default; 512 is the other instantiation;
+                                          // one more warp feeds the TMA ring
+constexpr int kDsmMaxThreads = 512;
 constexpr int kDsmTileNnz = 1024;
-constexpr int kDsmTileRows = 64;    // = kDsmThreads / 4: at least 4 lanes per row
+constexpr int kDsmTileRows = 128;   // = kDsmMaxThreads / 4: at least 4 lanes per row
 constexpr int kDsmStages = 6;
 constexpr int kDsmBurst = 8;        // entries per lane gathered back to back
 constexpr int kDsmMaxDynSmem = 229376;   // 224 KB of dynamic shared memory (227 KB minus the static part)
@@ -161,8 +162,8 @@ __device__ __forceinline__ bool dsm_try_wait(uint32_t addr, uint32_t parity) {
 // fence.acq_rel.cluster on the producer / consumer side (the PTX-model-complete protocol; ptxas turns each into
 // MEMBAR.ALL.GPU, +0.65 us per wavefront each, measured) for A/B runs; bit 2: wait with try_wait (hardware suspend)
 // instead of spinning on test_wait.
-template <int LOG_NC, int T>
-__global__ void __launch_bounds__(kDsmBlock, 1)
+template <int LOG_NC, int T, int BS>
+__global__ void __launch_bounds__(BS + 32, 1)
     gs_dsm_kernel(int n, int ntiles, int nlev, const int4* __restrict__ meta, const int2* __restrict__ aux,
                   const int* __restrict__ rowptr, const int* __restrict__ code, const double* __restrict__ val,
                   const int* __restrict__ rowof, const int* __restrict__ own_off, const int* __restrict__ wave_tiles, double* x,
@@ -170,11 +171,11 @@ __global__ void __launch_bounds__(kDsmBlock, 1)
                   int* __restrict__ status, unsigned long long* __restrict__ dbg) {
   constexpr int NC = 1 << LOG_NC;
   constexpr bool LOCAL = NC == 1;
+  constexpr int kDsmThreads = BS, kDsmBlock = BS + 32;   // (shadow the defaults)
   extern __shared__ __align__(128) unsigned char dsm_smem[];
   DsmStage* st = reinterpret_cast<DsmStage*>(dsm_smem);
   double* xs = reinterpret_cast<double*>(dsm_smem + kDsmStages * sizeof(DsmStage));
   __shared__ __align__(8) uint64_t full[kDsmStages];    // stage filled (TMA bytes landed)
-  __shared__ __align__(8) uint64_t empty[kDsmStages];   // stage released by the consumers
   __shared__ uint32_t xaddr[NC];     // shared::cluster address of every CTA's x slots
   __shared__ uint32_t wbaddr[NC];    // shared::cluster address of every CTA's wavefront barriers
   __shared__ double s_zero;          // what idle slots of a gather burst read
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(kDsmBlock, 1)
 
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kDsmStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kDsmStages; ++s) mbar_init(&full[s], 1);
     s_zero = 0.0;
   }
   if (NC > 1)
@@ -208,16 +209,17 @@ __global__ void __launch_bounds__(kDsmBlock, 1)
 
   if (tid >= kDsmThreads) {
     // ---- producer warp: keeps the ring full; nothing of the matrix stream is on the consumers' critical path ----
-    if (tid == kDsmThreads) {
+    {
       int4 mt = nown > 0 ? __ldg(meta + tile_of(0)) : make_int4(0, 0, 0, 0);
       int ps = 0;
-      uint32_t pphase = 1;   // parity of "released for the previous fill"; the first fill of a stage does not wait
       for (int i = 0; i < nown; ++i) {
         const int4 mn = i + 1 < nown ? __ldg(meta + tile_of(i + 1)) : mt;
-        if (i >= kDsmStages) mbar_wait(&empty[ps], pphase);
-        dsm_issue(st[ps], &full[ps], mt, rowptr, code, val, b);
+        if (i >= kDsmStages) {   // the consumers released the stage: bar.arrive there, bar.sync here (named barrier 2 + stage)
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + ps), "n"(kDsmBlock) : "memory");
+        }
+        if (tid == kDsmThreads) dsm_issue(st[ps], &full[ps], mt, rowptr, code, val, b);
         mt = mn;
-        if (++ps == kDsmStages) { ps = 0; pphase ^= 1u; }
+        if (++ps == kDsmStages) ps = 0;
       }
     }
   } else {
@@ -324,6 +326,7 @@ __global__ void __launch_bounds__(kDsmBlock, 1)
       *slot = sor ? __dadd_rn(__dmul_rn(1.0 - omega, *slot), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kDsmThreads) : "memory");   // consumers: the tile is relaxed (its x is in my shared memory), stage s is free
+    if (i + kDsmStages < nown) asm volatile("bar.arrive %0, %1;" ::"r"(2 + s), "n"(kDsmBlock) : "memory");   // tell the producer warp (non-blocking)
     if (stamp) stamp[5] = (unsigned long long)clock64();
     if (tid < 32) {
       if (NC > 1) {
@@ -331,7 +334,6 @@ __global__ void __launch_bounds__(kDsmBlock, 1)
         else dsm_fence_cta();
         if (tid < NC) dsm_arrive_remote(wbaddr[tid] + 8u * (uint32_t)wf);
       }
-      if (tid == 0) mbar_arrive(&empty[s]);
       if (stamp) { stamp[6] = (unsigned long long)clock64(); stamp[7] = global_ns(); }
     }
     if (++s == kDsmStages) { s = 0; parity ^= 1u; }

@@ -490,7 +490,7 @@ struct SmootherMatrix {
   int4* dsm_meta = nullptr;
   int2* dsm_aux = nullptr;
   int *dsm_code = nullptr, *dsm_rowof = nullptr, *dsm_own_off = nullptr, *dsm_wave_tiles = nullptr;
-  int dsm_ntiles = 0, dsm_lanes = 0, dsm_log_nc = 0, dsm_slots_max = 0;
+  int dsm_ntiles = 0, dsm_lanes = 0, dsm_threads = 256, dsm_log_nc = 0, dsm_slots_max = 0;
   int* dsm_status = nullptr;
   uint4* mail = nullptr;
   unsigned* mail_ctl = nullptr;
@@ -561,7 +561,8 @@ struct SmootherMatrix {
       int T = 4;
       while (T < 32 && kDsmBurst * T < 1.6 * mean) T *= 2;   // one gather burst covers all but the longest rows
       T = std::min(32, std::max(4, env_int("B200AMG_DSM_LANES", T)));
-      const int G = kDsmThreads / T;
+      const int threads = env_int("B200AMG_DSM_THREADS", kDsmThreads) == 512 ? 512 : 256;
+      const int G = threads / T;
       std::vector<int4> tm;
       std::vector<int2> ta;
       bool ok = true;
@@ -624,13 +625,14 @@ struct SmootherMatrix {
           dsm_wave_tiles = dev_upload(wave_tiles);
           dsm_ntiles = (int)tm.size();
           dsm_lanes = T;
+          dsm_threads = threads;
           dsm_log_nc = lnc;
           dsm_slots_max = own_off[NC + 1];
           dsm_status = dev_alloc<int>(4);
           CUDA_OK(cudaMemset(dsm_status, 0, 4 * sizeof(int)));
           if (env_int("B200AMG_GS_DSM_VERBOSE", 0))
-            fprintf(stderr, "[b200amg] dsm plan: n=%lld nnz=%lld wavefronts=%d lanes=%d ctas=%d tiles=%d slots/cta=%d smem=%zu\n",
-                    (long long)n, (long long)w.nnz(), nl, T, NC, dsm_ntiles, dsm_slots_max, dsm_smem_bytes(dsm_slots_max, nl));
+            fprintf(stderr, "[b200amg] dsm plan: n=%lld nnz=%lld wavefronts=%d lanes=%d threads=%d ctas=%d tiles=%d slots/cta=%d smem=%zu\n",
+                    (long long)n, (long long)w.nnz(), nl, T, threads, NC, dsm_ntiles, dsm_slots_max, dsm_smem_bytes(dsm_slots_max, nl));
         }
       }
     }
@@ -766,8 +768,10 @@ struct b200amg_hierarchy {
                                       // 2.4-3.9 us per wavefront vs 2.2-2.5 for the counter sweep, so off by default
   int64_t gs_cluster_rows = 380000;
   int gs_cluster_log_nc = 3, gs_cluster_threads = 256;
-  int gs_dsm = 0;                     // 1: one-cluster sweep with x in distributed shared memory + per-wavefront arrival
-                                      // counters in shared memory (dsm_gs.cuh) on every level it fits
+  int gs_dsm = 1;                     // 1: one-cluster sweep with x in distributed shared memory + per-wavefront mbarriers
+                                      // (dsm_gs.cuh) on narrow-wavefront levels that fit gs_dsm_max_log_nc CTAs; 2: required
+  int gs_dsm_max_log_nc = 2;          // measured (256^3 RS hierarchy, SGS ms): 1 CTA 2.56 -> 1.83 (5 195 rows), 4 CTAs
+                                      // 7.42 -> 5.63 (38 260 rows), 16 CTAs 4.69 -> 5.16 (228 538 rows): up to 4 CTAs by default
   int gs_dsm_fence = 0;               // bit 0 / 1: cluster-scope fence on the producer / consumer side of the hand-off
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
@@ -1071,14 +1075,14 @@ static bool launch_gs_cluster(H* h, const SmootherMatrix& M, const DevCsr& A, co
   return launch_gs_cluster_T<4, 1024>(h, M, A, sc, x, b, w, sor);
 }
 // attributes + schedulability of one instantiation, probed once (at b200amg_create: never inside a stream capture)
-template <int LOG_NC, int T>
+template <int LOG_NC, int T, int BS>
 static int dsm_state() {
   static int state = 0;   // 1 usable, -1 not schedulable on this device
   if (state != 0) return state;
   constexpr int NC = 1 << LOG_NC;
   cudaLaunchConfig_t probe = {};
   probe.gridDim = dim3(NC, 1, 1);
-  probe.blockDim = dim3(kDsmBlock, 1, 1);
+  probe.blockDim = dim3(BS + 32, 1, 1);
   probe.dynamicSmemBytes = kDsmMaxDynSmem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1088,9 +1092,9 @@ static int dsm_state() {
   probe.attrs = attr;
   probe.numAttrs = NC > 1 ? 1 : 0;
   int nclusters = 1;
-  if (cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsmMaxDynSmem) != cudaSuccess ||
-      (NC > 8 && cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
-      (NC > 1 && (cudaOccupancyMaxActiveClusters(&nclusters, gs_dsm_kernel<LOG_NC, T>, &probe) != cudaSuccess || nclusters < 1))) {
+  if (cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsmMaxDynSmem) != cudaSuccess ||
+      (NC > 8 && cudaFuncSetAttribute(gs_dsm_kernel<LOG_NC, T, BS>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+      (NC > 1 && (cudaOccupancyMaxActiveClusters(&nclusters, gs_dsm_kernel<LOG_NC, T, BS>, &probe) != cudaSuccess || nclusters < 1))) {
     cudaGetLastError();
     state = -1;
   } else {
@@ -1099,18 +1103,21 @@ static int dsm_state() {
   return state;
 }
 template <int LOG_NC>
-static void dsm_init_nc() { dsm_state<LOG_NC, 4>(); dsm_state<LOG_NC, 8>(); dsm_state<LOG_NC, 16>(); dsm_state<LOG_NC, 32>(); }
+static void dsm_init_nc() {
+  dsm_state<LOG_NC, 4, 256>(); dsm_state<LOG_NC, 8, 256>(); dsm_state<LOG_NC, 16, 256>(); dsm_state<LOG_NC, 32, 256>();
+  dsm_state<LOG_NC, 4, 512>(); dsm_state<LOG_NC, 8, 512>(); dsm_state<LOG_NC, 16, 512>(); dsm_state<LOG_NC, 32, 512>();
+}
 static void dsm_kernels_init() { dsm_init_nc<0>(); dsm_init_nc<1>(); dsm_init_nc<2>(); dsm_init_nc<3>(); dsm_init_nc<4>(); }
 // ---- one-cluster sweep, x in distributed shared memory, dataflow hand-off through shared memory (dsm_gs.cuh) ----
-template <int LOG_NC, int T>
+template <int LOG_NC, int T, int BS>
 static bool launch_gs_dsm_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
                             int sor) {
   constexpr int NC = 1 << LOG_NC;
   const size_t smem = dsm_smem_bytes(M.dsm_slots_max, M.nlev);
-  if (dsm_state<LOG_NC, T>() < 0 || smem > (size_t)kDsmMaxDynSmem) return false;
+  if (dsm_state<LOG_NC, T, BS>() < 0 || smem > (size_t)kDsmMaxDynSmem) return false;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(NC, 1, 1);
-  cfg.blockDim = dim3(kDsmBlock, 1, 1);
+  cfg.blockDim = dim3(BS + 32, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
@@ -1120,7 +1127,7 @@ static bool launch_gs_dsm_T(H* h, const SmootherMatrix& M, const DevCsr& A, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NC > 1 ? 1 : 0;
-  CUDA_OK(cudaLaunchKernelEx(&cfg, gs_dsm_kernel<LOG_NC, T>, (int)M.n, M.dsm_ntiles, M.nlev, (const int4*)M.dsm_meta,
+  CUDA_OK(cudaLaunchKernelEx(&cfg, gs_dsm_kernel<LOG_NC, T, BS>, (int)M.n, M.dsm_ntiles, M.nlev, (const int4*)M.dsm_meta,
                              (const int2*)M.dsm_aux, (const int*)A.ptr, (const int*)M.dsm_code, (const double*)A.val,
                              (const int*)M.dsm_rowof, (const int*)M.dsm_own_off, (const int*)M.dsm_wave_tiles, x, b, w, sor,
                              sc.backward, h->opaque_zero,
@@ -1131,11 +1138,20 @@ static bool launch_gs_dsm_T(H* h, const SmootherMatrix& M, const DevCsr& A, cons
 template <int LOG_NC>
 static bool launch_gs_dsm_NC(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b,
                              double w, int sor) {
+  if (M.dsm_threads == 512) {
+    switch (M.dsm_lanes) {
+      case 4: return launch_gs_dsm_T<LOG_NC, 4, 512>(h, M, A, sc, x, b, w, sor);
+      case 8: return launch_gs_dsm_T<LOG_NC, 8, 512>(h, M, A, sc, x, b, w, sor);
+      case 16: return launch_gs_dsm_T<LOG_NC, 16, 512>(h, M, A, sc, x, b, w, sor);
+      case 32: return launch_gs_dsm_T<LOG_NC, 32, 512>(h, M, A, sc, x, b, w, sor);
+      default: return false;
+    }
+  }
   switch (M.dsm_lanes) {
-    case 4: return launch_gs_dsm_T<LOG_NC, 4>(h, M, A, sc, x, b, w, sor);
-    case 8: return launch_gs_dsm_T<LOG_NC, 8>(h, M, A, sc, x, b, w, sor);
-    case 16: return launch_gs_dsm_T<LOG_NC, 16>(h, M, A, sc, x, b, w, sor);
-    case 32: return launch_gs_dsm_T<LOG_NC, 32>(h, M, A, sc, x, b, w, sor);
+    case 4: return launch_gs_dsm_T<LOG_NC, 4, 256>(h, M, A, sc, x, b, w, sor);
+    case 8: return launch_gs_dsm_T<LOG_NC, 8, 256>(h, M, A, sc, x, b, w, sor);
+    case 16: return launch_gs_dsm_T<LOG_NC, 16, 256>(h, M, A, sc, x, b, w, sor);
+    case 32: return launch_gs_dsm_T<LOG_NC, 32, 256>(h, M, A, sc, x, b, w, sor);
     default: return false;
   }
 }
@@ -1192,7 +1208,8 @@ static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const 
 }
 static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   const DevCsr& A = M.walked();
-  if (h->gs_mode >= 1 && h->gs_dsm && M.d_fwd_lvlptr && !(sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width)) {
+  if (h->gs_mode >= 1 && h->gs_dsm && M.d_fwd_lvlptr && M.dsm_ntiles > 0 && M.dsm_log_nc <= h->gs_dsm_max_log_nc &&
+      !(sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width)) {
     if (launch_gs_dsm(h, M, A, sc, x, b, w, sor)) return;
     REQUIRE(h->gs_dsm < 2 || M.dsm_ntiles <= 0, B200AMG_ERR_CUDA, "the distributed-shared-memory sweep could not be launched (n = %lld, %d CTAs)",
             (long long)M.n, 1 << M.dsm_log_nc);
@@ -1712,7 +1729,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_tile_any_lanes = env_int("B200AMG_GS_TILE_ANY_LANES", 1);
   h->gs_counter_mail = env_int("B200AMG_GS_COUNTER_MAIL", 1);
   h->gs_cluster = env_int("B200AMG_GS_CLUSTER", 0);
-  h->gs_dsm = env_int("B200AMG_GS_DSM", 0);
+  h->gs_dsm = env_int("B200AMG_GS_DSM", 1);
+  h->gs_dsm_max_log_nc = env_int("B200AMG_GS_DSM_MAX_CTAS_LOG2", 2);
   h->gs_dsm_fence = env_int("B200AMG_GS_DSM_FENCE", 0);
   h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
@@ -2434,6 +2452,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_CLUSTER: h->gs_cluster = (int)value; break;
     case B200AMG_OPT_GS_DSM: h->gs_dsm = (int)value; break;
     case B200AMG_OPT_GS_DSM_FENCE: h->gs_dsm_fence = (int)value; break;
+    case B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2: h->gs_dsm_max_log_nc = (int)value; break;
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
       h->part_levels = std::max(1, (int)value);

@@ -212,14 +212,15 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
  * GS_GATE_SLEEP tune the hand-off.  PART_LEVELS (default 1; before the first add_level of a partitioned handle):
  * how many of the finest levels are split by rows over the ranks (a level below a partitioned one inherits its parent's
  * coarse-row ownership, so restriction needs no communication and prolongation one more halo exchange).
- * GS_DSM (default 0): 1 = levels whose x fits the shared memory of one thread-block cluster (<= ~260 000 rows) and whose
- * wavefronts are narrower than GS_MAIL_MIN_WIDTH are swept by ONE cluster with x in distributed shared memory
- * (csrc/device/dsm_gs.cuh); GS_DSM_FENCE bit 0 / bit 1 add a cluster-scope fence on the producer / consumer side of its hand-off.
+ * GS_DSM (default 1): levels whose wavefronts are narrower than GS_MAIL_MIN_WIDTH and whose x fits the shared memory of a
+ * thread-block cluster of <= 2^GS_DSM_MAX_CTAS_LOG2 CTAs (default 2: 4 CTAs, ~68 000 rows; up to 4: 16 CTAs, ~260 000 rows)
+ * are swept by ONE cluster with x in distributed shared memory (csrc/device/dsm_gs.cuh); 0 = the GS_MODE kernels on every
+ * level.  GS_DSM_FENCE bit 0 / bit 1 add a cluster-scope fence on the producer / consumer side of its hand-off.
  * Cycle graphs already captured keep the values they were captured with. */
 enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1, B200AMG_OPT_STREAM_CHUNK = 2, B200AMG_OPT_GS_MODE = 3, B200AMG_OPT_GS_ACQUIRE = 4, B200AMG_OPT_GS_POLL_SLEEP = 5,
        B200AMG_OPT_GS_GATE_SLEEP = 6, B200AMG_OPT_GS_CTA_ROWS = 7,
        B200AMG_OPT_GS_MAIL_MIN_WIDTH = 8, B200AMG_OPT_GS_CLUSTER = 9,
-       B200AMG_OPT_PART_LEVELS = 12, B200AMG_OPT_GS_DSM = 13, B200AMG_OPT_GS_DSM_FENCE = 14 };
+       B200AMG_OPT_PART_LEVELS = 12, B200AMG_OPT_GS_DSM = 13, B200AMG_OPT_GS_DSM_FENCE = 14, B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2 = 15 };
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
 int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
 /* Diagnostics: run one dataflow Gauss-Seidel sweep (forward / backward) of `level` on the level's

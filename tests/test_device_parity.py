@@ -512,6 +512,7 @@ def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence):
     reference's sequential Gauss-Seidel / SOR sweeps (forward, backward, symmetric; Hermitian and NoSymmetry walks),
     on stencil rows, irregular RS coarse operators and a nonsymmetric matrix; then whole cycles through it."""
     monkeypatch.setenv("B200AMG_GS_DSM", "2")
+    monkeypatch.setenv("B200AMG_GS_DSM_MAX_CTAS_LOG2", "4")
     monkeypatch.setenv("B200AMG_GS_DSM_FENCE", str(fence))
     if log_nc >= 0:
         monkeypatch.setenv("B200AMG_GS_DSM_LOG_NC", str(log_nc))

@@ -64,6 +64,7 @@ if args.smoother == "gs":
     dev.set_option(3, 2)
     for fence in (0, 4, 1):
         dev.set_option(13, 1)
+        dev.set_option(15, 4)
         dev.set_option(14, fence)
         for lv in range(dev.nlevels - 1):
             info = dev.level_info(lv)
