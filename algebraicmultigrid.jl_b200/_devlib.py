@@ -30,7 +30,7 @@ SYMBOLS = [
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
-    "b200amg_partition_info", "b200amg_partition_plan",
+    "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child",
 ]
 
 
@@ -106,6 +106,8 @@ def lib():
             "b200amg_nccl_unique_id": [vp, i64],
             "b200amg_partition_info": [vp] + [C.POINTER(i64)] * 8,
             "b200amg_partition_plan": [pcsc, pcsc, pcsc, i32, i32, vp, vp, vp, C.POINTER(i64), vp, vp, C.POINTER(i64), vp, vp, vp, i64],
+            "b200amg_partition_plan_child": [pcsc, pcsc, pcsc, pcsc, vp, vp, i32, i32, vp, vp, vp, C.POINTER(i64), vp, vp, C.POINTER(i64),
+                                             vp, vp, vp, i64],
             "b200amg_debug_gs_timeline": [vp, i32, i32, vp, i64, C.POINTER(i64)],
         }
         for name, args in sigs.items():
@@ -134,8 +136,9 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
-def partition_plan(level, rank, world):
-    """Host-only partition plan of one ``Level`` (``b200amg_partition_plan``) as a dict of numpy arrays."""
+def partition_plan(level, rank, world, parent_level=None, parent_plan=None):
+    """Host-only partition plan of one ``Level`` (``b200amg_partition_plan``) as a dict of numpy arrays; with
+    ``parent_level`` / ``parent_plan`` the plan of a level below a partitioned one (``b200amg_partition_plan_child``)."""
     keep = []
     a, p, r = csc_desc(level.A, keep), csc_desc(level.P, keep), csc_desc(level.R, keep)
     n = level.A.n
@@ -145,10 +148,15 @@ def partition_plan(level, rank, world):
            "send_idx": np.zeros(cap, np.int32), "send_off": np.zeros(world + 1, np.int32),
            "cx_lo": np.zeros(world, np.int64), "cx_hi": np.zeros(world, np.int64)}
     nhalo, nsend = C.c_int64(0), C.c_int64(0)
-    _check(lib().b200amg_partition_plan(C.byref(a), C.byref(p), C.byref(r), rank, world, _ptr(out["row_split"]),
-                                        _ptr(out["coarse_split"]), _ptr(out["halo_cols"]), C.byref(nhalo), _ptr(out["recv_off"]),
-                                        _ptr(out["send_idx"]), C.byref(nsend), _ptr(out["send_off"]), _ptr(out["cx_lo"]),
-                                        _ptr(out["cx_hi"]), cap))
+    tail = (rank, world, _ptr(out["row_split"]), _ptr(out["coarse_split"]), _ptr(out["halo_cols"]), C.byref(nhalo), _ptr(out["recv_off"]),
+            _ptr(out["send_idx"]), C.byref(nsend), _ptr(out["send_off"]), _ptr(out["cx_lo"]), _ptr(out["cx_hi"]), C.c_int64(cap))
+    if parent_level is None:
+        _check(lib().b200amg_partition_plan(C.byref(a), C.byref(p), C.byref(r), *tail))
+    else:
+        pp = csc_desc(parent_level.P, keep)
+        prs = np.ascontiguousarray(parent_plan["row_split"], dtype=np.int64)
+        pcs = np.ascontiguousarray(parent_plan["coarse_split"], dtype=np.int64)
+        _check(lib().b200amg_partition_plan_child(C.byref(a), C.byref(p), C.byref(r), C.byref(pp), _ptr(prs), _ptr(pcs), *tail))
     out["halo_cols"] = out["halo_cols"][: nhalo.value].copy()
     out["send_idx"] = out["send_idx"][: nsend.value].copy()
     return out

@@ -776,6 +776,7 @@ struct b200amg_hierarchy {
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
+  int gs_poll_masked = 1;             // TMA-fed mailbox sweep: poll only the mailboxes a row still waits for
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
   int gs_acquire = 0;     // consumer-side acquire of the dataflow sweep: 0 none (see stream.cuh), 1 ld.acquire, 2 fence
@@ -1015,7 +1016,7 @@ static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, con
   count_launch(h);
   gs_tile_kernel<T><<<ctas, kGsTileThreads, kStages * sizeof(GsCtaStage), h->stream>>>(
       M.gs_ntiles, M.gs_meta, M.gs_tile_wave, M.nlev, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor, sc.backward, h->opaque_zero,
-      h->gs_poll_sleep, h->gs_gate_sleep);
+      h->gs_poll_sleep, h->gs_gate_sleep, h->gs_poll_masked);
   count_launch(h);
 }
 static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
@@ -1734,6 +1735,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_dsm_fence = env_int("B200AMG_GS_DSM_FENCE", 0);
   h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
+  h->gs_poll_masked = env_int("B200AMG_GS_POLL_MASKED", 1);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
@@ -1936,10 +1938,10 @@ int32_t b200amg_nccl_unique_id(void* out, int64_t cap) {
 // Host-only: the plan one rank of a `world`-way partition would use (no device needed; what the CPU
 // world_size-2 tests exercise).  Array capacities: row_split/coarse_split/recv_off/send_off world+1,
 // cx_lo/cx_hi world, halo_cols/send_idx `cap` entries.
-int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, int32_t rank, int32_t world,
-                               int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
-                               int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap) {
-  API_BEGIN
+static void partition_plan_impl(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, const b200amg_csc_t* parentP,
+                                const int64_t* parent_row_split, const int64_t* parent_coarse_split, int32_t rank, int32_t world,
+                                int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                                int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap) {
   REQUIRE(A && P && R && row_split && coarse_split && halo_cols && nhalo && recv_off && send_idx && nsend && send_off && cx_lo && cx_hi,
           B200AMG_ERR_BAD_ARG, "null argument");
   REQUIRE(world >= 1 && rank >= 0 && rank < world, B200AMG_ERR_BAD_ARG, "bad rank / world");
@@ -1947,7 +1949,17 @@ int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, c
   HostCsr hA = transpose(hAt);
   const bool sym = bit_equal(hA, hAt);
   HostCsr hP = stage_operator_by_rows(P), hR = stage_operator_by_rows(R);
-  PartPlan pl = make_part_plan(rank, world, hA, sym ? nullptr : &hAt, hR, hP);
+  PartPlan pl;
+  if (parentP) {
+    REQUIRE(parent_row_split && parent_coarse_split, B200AMG_ERR_BAD_ARG, "a child plan needs the parent's row and coarse splits");
+    HostCsr hPP = stage_operator_by_rows(parentP);
+    REQUIRE(hPP.ncols == hA.nrows, B200AMG_ERR_DIM_MISMATCH, "the parent's P has %lld columns, this level %lld rows", (long long)hPP.ncols,
+            (long long)hA.nrows);
+    const std::vector<int64_t> given(parent_coarse_split, parent_coarse_split + world + 1), prs(parent_row_split, parent_row_split + world + 1);
+    pl = make_part_plan(rank, world, hA, sym ? nullptr : &hAt, hR, hP, &given, &hPP, &prs);
+  } else {
+    pl = make_part_plan(rank, world, hA, sym ? nullptr : &hAt, hR, hP);
+  }
   REQUIRE((int64_t)pl.halo_cols.size() <= cap && (int64_t)pl.send_idx.size() <= cap, B200AMG_ERR_BAD_ARG, "capacity too small");
   std::copy(pl.row_split.begin(), pl.row_split.end(), row_split);
   std::copy(pl.coarse_split.begin(), pl.coarse_split.end(), coarse_split);
@@ -1959,6 +1971,25 @@ int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, c
   std::copy(pl.cx_hi_all.begin(), pl.cx_hi_all.end(), cx_hi);
   *nhalo = pl.nhalo;
   *nsend = (int64_t)pl.send_idx.size();
+}
+
+int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, int32_t rank, int32_t world,
+                               int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                               int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap) {
+  API_BEGIN
+  partition_plan_impl(A, P, R, nullptr, nullptr, nullptr, rank, world, row_split, coarse_split, halo_cols, nhalo, recv_off, send_idx, nsend,
+                      send_off, cx_lo, cx_hi, cap);
+  API_END
+}
+
+int32_t b200amg_partition_plan_child(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, const b200amg_csc_t* parent_P,
+                                     const int64_t* parent_row_split, const int64_t* parent_coarse_split, int32_t rank, int32_t world,
+                                     int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                                     int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap) {
+  API_BEGIN
+  REQUIRE(parent_P, B200AMG_ERR_BAD_ARG, "null parent P");
+  partition_plan_impl(A, P, R, parent_P, parent_row_split, parent_coarse_split, rank, world, row_split, coarse_split, halo_cols, nhalo,
+                      recv_off, send_idx, nsend, send_off, cx_lo, cx_hi, cap);
   API_END
 }
 
@@ -2453,6 +2484,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_DSM: h->gs_dsm = (int)value; break;
     case B200AMG_OPT_GS_DSM_FENCE: h->gs_dsm_fence = (int)value; break;
     case B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2: h->gs_dsm_max_log_nc = (int)value; break;
+    case 16: h->gs_poll_masked = (int)value; break;   // experiment knob (tools/tune_kernels.py)
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
       h->part_levels = std::max(1, (int)value);

@@ -321,6 +321,37 @@ __device__ __forceinline__ void ld_mail8(uint4 (&m)[8], const uint4* const (&a)[
       : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7])
       : "memory");
 }
+// the same burst, but only the slots named in `mask` are loaded (the others keep their contents and cost no L2 request):
+// a row polls ONLY the mailboxes it still waits for
+__device__ __forceinline__ void ld_mail8_masked(uint4 (&m)[8], const uint4* const (&a)[8], unsigned mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q0, q1, q2, q3, q4, q5, q6, q7;\n\t"
+      ".reg .b32 t;\n\t"
+      "and.b32 t, %40, 1;\n\t   setp.ne.b32 q0, t, 0;\n\t"
+      "and.b32 t, %40, 2;\n\t   setp.ne.b32 q1, t, 0;\n\t"
+      "and.b32 t, %40, 4;\n\t   setp.ne.b32 q2, t, 0;\n\t"
+      "and.b32 t, %40, 8;\n\t   setp.ne.b32 q3, t, 0;\n\t"
+      "and.b32 t, %40, 16;\n\t  setp.ne.b32 q4, t, 0;\n\t"
+      "and.b32 t, %40, 32;\n\t  setp.ne.b32 q5, t, 0;\n\t"
+      "and.b32 t, %40, 64;\n\t  setp.ne.b32 q6, t, 0;\n\t"
+      "and.b32 t, %40, 128;\n\t setp.ne.b32 q7, t, 0;\n\t"
+      "@q0 ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%32];\n\t"
+      "@q1 ld.relaxed.gpu.global.v4.u32 {%4, %5, %6, %7}, [%33];\n\t"
+      "@q2 ld.relaxed.gpu.global.v4.u32 {%8, %9, %10, %11}, [%34];\n\t"
+      "@q3 ld.relaxed.gpu.global.v4.u32 {%12, %13, %14, %15}, [%35];\n\t"
+      "@q4 ld.relaxed.gpu.global.v4.u32 {%16, %17, %18, %19}, [%36];\n\t"
+      "@q5 ld.relaxed.gpu.global.v4.u32 {%20, %21, %22, %23}, [%37];\n\t"
+      "@q6 ld.relaxed.gpu.global.v4.u32 {%24, %25, %26, %27}, [%38];\n\t"
+      "@q7 ld.relaxed.gpu.global.v4.u32 {%28, %29, %30, %31}, [%39];\n\t"
+      "}"
+      : "+r"(m[0].x), "+r"(m[0].y), "+r"(m[0].z), "+r"(m[0].w), "+r"(m[1].x), "+r"(m[1].y), "+r"(m[1].z), "+r"(m[1].w),
+        "+r"(m[2].x), "+r"(m[2].y), "+r"(m[2].z), "+r"(m[2].w), "+r"(m[3].x), "+r"(m[3].y), "+r"(m[3].z), "+r"(m[3].w),
+        "+r"(m[4].x), "+r"(m[4].y), "+r"(m[4].z), "+r"(m[4].w), "+r"(m[5].x), "+r"(m[5].y), "+r"(m[5].z), "+r"(m[5].w),
+        "+r"(m[6].x), "+r"(m[6].y), "+r"(m[6].z), "+r"(m[6].w), "+r"(m[7].x), "+r"(m[7].y), "+r"(m[7].z), "+r"(m[7].w)
+      : "l"(a[0]), "l"(a[1]), "l"(a[2]), "l"(a[3]), "l"(a[4]), "l"(a[5]), "l"(a[6]), "l"(a[7]), "r"(mask)
+      : "memory");
+}
 // tasks[t] = {first row, rows, wavefront in sweep order, tasks of the previous wavefront}
 // counters[0] = ticket, counters[(1 + w) * kGsCounterStride] = finished tasks of wavefront w (zeroed before the launch)
 // MAIL: rows are additionally published as 16-byte {value, epoch} mailboxes (see gs_mail_kernel) and the
@@ -848,7 +879,7 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
     gs_tile_kernel(int ntiles, const int4* __restrict__ meta, const int* __restrict__ tile_wave, int nlev, unsigned* ctl,
                    const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, double* x,
                    const double* __restrict__ b, uint4* mail, double omega, int sor, int backward, int opaque_zero,
-                   int poll_sleep, int gate_sleep) {
+                   int poll_sleep, int gate_sleep, int poll_masked) {
   extern __shared__ __align__(128) unsigned char gs_tile_smem[];
   GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_tile_smem);
   __shared__ __align__(8) uint64_t full[kStages];
@@ -927,8 +958,12 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
         const uint4* a[kGsPrefetch];
         uint4 mm[kGsPrefetch];
 #pragma unroll
-        for (int j = 0; j < kGsPrefetch; ++j) a[j] = ((need >> j) & 1u) ? mail + c[j] : mail + (row >= 0 ? row : 0);
-        ld_mail8(mm, a);
+        for (int j = 0; j < kGsPrefetch; ++j) {
+          a[j] = ((need >> j) & 1u) ? mail + c[j] : mail + (row >= 0 ? row : 0);
+          mm[j] = make_uint4(0u, ~e, 0u, ~e);
+        }
+        if (poll_masked) ld_mail8_masked(mm, a, need);   // only the mailboxes still waited for: no poll traffic for the rest
+        else ld_mail8(mm, a);
         {
           unsigned dep = mm[0].y;
 #pragma unroll

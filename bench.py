@@ -197,7 +197,7 @@ def run_ours(args):
         uid = _devlib.nccl_unique_id() if rank == 0 else None
         box = [uid]
         dist.broadcast_object_list(box, src=0)
-        ml.partition(rank, world, box[0])
+        ml.partition(rank, world, box[0], levels=args.part_levels)
     t0 = time.time()
     dev = ml.device()
     t_upload = time.time() - t0
@@ -347,7 +347,8 @@ def run_ours(args):
         "config": {"workload": workload_name(args), "n": n, "nnz": nnz, "levels": dev.nlevels,
                    "l2": (f"inputs larger than L2: fine-level A is {12e-9 * nnz:.2f} GB, the hierarchy {12e-9 * sum(i['nnz_a'] for i in infos):.2f} GB, "
                           "126 MB of L2; every kernel of a cycle streams a different operator, no flush needed"),
-                   "parallelism": f"fine level row-partitioned x{world}" if world > 1 else "single GPU"},
+                   "parallelism": (f"{args.part_levels} finest level(s) row-partitioned x{world}, the rest on rank 0" if world > 1
+                                   else "single GPU")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
     }
     if world > 1:
@@ -375,6 +376,8 @@ def main():
     ap.add_argument("--method", default="rs", choices=["rs", "sa"])
     ap.add_argument("--smoother", default="gs", choices=["gs", "jacobi"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--part-levels", type=int, default=int(os.environ.get("B200AMG_PART_LEVELS", "3")),
+                    help="N > 1: how many of the finest levels are split by rows over the ranks")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

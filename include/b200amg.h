@@ -131,6 +131,15 @@ int32_t b200amg_partition_info(b200amg_handle_t h, int64_t* row_lo, int64_t* row
 int32_t b200amg_partition_plan(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, int32_t rank, int32_t world,
                                int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
                                int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap);
+/* The same for a level BELOW a partitioned one (B200AMG_OPT_PART_LEVELS > 1): its row blocks are the parent's
+ * coarse_split (so the parent's restriction writes straight into this level's owned b), and the entries of this
+ * level's x that the parent's owned rows of P reference are part of the halo (the prolongation reads them after one
+ * halo exchange).  parent_P: the prolongation of the level above; parent_row_split / parent_coarse_split: world + 1
+ * entries from the parent's plan. */
+int32_t b200amg_partition_plan_child(const b200amg_csc_t* A, const b200amg_csc_t* P, const b200amg_csc_t* R, const b200amg_csc_t* parent_P,
+                                     const int64_t* parent_row_split, const int64_t* parent_coarse_split, int32_t rank, int32_t world,
+                                     int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
+                                     int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap);
 /* builds device layouts (row-major operators, transposes, wavefront schedules), workspaces and
  * the captured cycle graphs. */
 int32_t b200amg_finalize(b200amg_handle_t h);

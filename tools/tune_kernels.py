@@ -59,7 +59,18 @@ if args.smoother == "gs":
             print(json.dumps({"gs_mode": mode, "level": lv, "n": n, "nnz": nnz, "wavefronts": info["wavefronts"],
                               "sgs_ms": round(ms, 4), "GBs": round(alg / ms / 1e6, 1),
                               "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}), flush=True)
-if args.smoother == "gs":
+if args.smoother == "gs" and os.environ.get("SWEEP_MASKED"):
+    dev.set_option(3, 2)
+    for masked in (1, 0, 1, 0):
+        dev.set_option(16, masked)
+        row = {}
+        for lv in range(min(3, dev.nlevels - 1)):
+            info = dev.level_info(lv)
+            ms = dev.time_kernel(lv, 2, reps=5)
+            row[lv] = {"sgs_ms": round(ms, 4), "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}
+        print(json.dumps({"poll_masked": masked, "levels": row}), flush=True)
+    dev.set_option(16, 1)
+if args.smoother == "gs" and not os.environ.get("SKIP_DSM"):
     # one-cluster sweep with x in distributed shared memory (cluster size fixed at upload: B200AMG_GS_DSM_LOG_NC)
     dev.set_option(3, 2)
     for fence in (0, 4, 1):
