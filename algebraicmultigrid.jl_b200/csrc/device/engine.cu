@@ -1016,7 +1016,7 @@ static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, con
   count_launch(h);
   gs_tile_kernel<T><<<ctas, kGsTileThreads, kStages * sizeof(GsCtaStage), h->stream>>>(
       M.gs_ntiles, M.gs_meta, M.gs_tile_wave, M.nlev, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor, sc.backward, h->opaque_zero,
-      h->gs_poll_sleep, h->gs_gate_sleep, h->gs_poll_masked);
+      h->gs_poll_sleep, h->gs_gate_sleep, h->gs_poll_masked, h->gs_debug);
   count_launch(h);
 }
 static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
@@ -2521,8 +2521,10 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   Level& L = *h->levels[level];
   const DevSchedule& sc = backward ? L.M.bwd : L.M.fwd;
   REQUIRE(sc.built, B200AMG_ERR_STATE, "no Gauss-Seidel schedule on this level");
-  const bool dsm = h->gs_dsm && L.M.dsm_ntiles > 0;   // stamps of the distributed-shared-memory sweep: 8 per tile (dsm_gs.cuh)
-  const int64_t words = (int64_t)(dsm ? L.M.dsm_ntiles : sc.ntasks) * 8;
+  const bool wide = sc.nlev > 0 && L.M.n / sc.nlev >= h->gs_mail_min_width;
+  const bool dsm = !wide && h->gs_dsm && L.M.dsm_ntiles > 0 && L.M.dsm_log_nc <= h->gs_dsm_max_log_nc;   // 8 stamps per tile (dsm_gs.cuh)
+  const bool tile = !dsm && wide && h->gs_mode == 2 && L.M.mail && L.M.gs_ntiles > 0;                    // 8 stamps per tile (gs_tile_kernel)
+  const int64_t words = (int64_t)(dsm ? L.M.dsm_ntiles : tile ? L.M.gs_ntiles : sc.ntasks) * 8;
   REQUIRE(cap >= words, B200AMG_ERR_BAD_ARG, "timeline buffer too small (%lld needed)", (long long)words);
   unsigned long long* d = dev_alloc<unsigned long long>(words);
   CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)words, h->stream));
@@ -2531,12 +2533,13 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   double* x = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
   const double* b = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
   if (dsm) REQUIRE(launch_gs_dsm(h, L.M, L.M.walked(), sc, x, b, L.pre.omega, sor), B200AMG_ERR_CUDA, "dsm sweep not launchable");
+  else if (tile) launch_gs_tile(h, L.M, L.M.walked(), sc, x, b, L.pre.omega, sor);
   else launch_dataflow(h, L.M.walked(), sc, x, b, L.pre.omega, sor);
   h->gs_debug = nullptr;
   CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   cudaFree(d);
-  *ntasks = dsm ? L.M.dsm_ntiles : sc.ntasks;
+  *ntasks = dsm ? L.M.dsm_ntiles : tile ? L.M.gs_ntiles : sc.ntasks;
   API_END
 }
 

@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
     gs_tile_kernel(int ntiles, const int4* __restrict__ meta, const int* __restrict__ tile_wave, int nlev, unsigned* ctl,
                    const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, double* x,
                    const double* __restrict__ b, uint4* mail, double omega, int sor, int backward, int opaque_zero,
-                   int poll_sleep, int gate_sleep, int poll_masked) {
+                   int poll_sleep, int gate_sleep, int poll_masked, unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char gs_tile_smem[];
   GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_tile_smem);
   __shared__ __align__(8) uint64_t full[kStages];
@@ -909,11 +909,15 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
     const int4 m = __ldg(meta + tile);
     const int wf = __ldg(tile_wave + tile);
     const int w = backward ? nlev - 1 - wf : wf;   // wavefront in sweep order
+    unsigned long long* stamp = (dbg && tid == 0) ? dbg + 8 * (size_t)tile : nullptr;   // diagnostics (gs_timeline): thread 0's view
+    unsigned long long polls = 0;
+    if (stamp) { stamp[0] = global_ns(); stamp[7] = (unsigned long long)w; }
     const int ka = m.z & ~3, ra = m.x & ~3;
     constexpr int G = kGsTileThreads / T;   // rows relaxed per pass
     const int nrows = m.y - m.x;
     const double xold0 = (g < nrows && lane == 0) ? __ldcg(x + m.x + g) : 0.0;   // first pass: requested before the waits
     mbar_wait(&full[s], parity);
+    if (stamp) stamp[1] = global_ns();
     const GsCtaStage& S = st[s];
     for (int rbase = 0; rbase < nrows; rbase += G) {   // rows of a tile are mutually independent
       const bool active = rbase + g < nrows;
@@ -954,7 +958,9 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
         }
         __syncthreads();
       }
+      if (stamp && rbase == 0) stamp[2] = global_ns();
       while (need) {
+        ++polls;
         const uint4* a[kGsPrefetch];
         uint4 mm[kGsPrefetch];
 #pragma unroll
@@ -980,6 +986,7 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
           }
         if (need && poll_sleep) __nanosleep(poll_sleep);
       }
+      if (stamp && rbase == 0) { stamp[3] = global_ns(); stamp[6] = polls; }
       __syncwarp();   // lanes leave the poll loop at different times: reconverge before the arithmetic
       double rsum = 0.0, d = 0.0;
 #pragma unroll
@@ -1019,9 +1026,11 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
         }
         st_mail(mail + row, xnew, e);
         __stcg(x + row, xnew);
+        if (stamp && rbase == 0) stamp[4] = global_ns();
       }
     }
     __syncthreads();   // stage s is free; the tile is published
+    if (stamp) stamp[5] = global_ns();
     if (tid == 0) {
       volatile unsigned* mine = ctl + (size_t)(2 + w) * kGsCounterStride;
       *mine = e;   // throttle hint only
