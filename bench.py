@@ -9,7 +9,8 @@ Gauss-Seidel smoothers, V-cycle.  A "step" is one iteration of `_solve!`
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 256]
                     [--method rs|sa] [--smoother gs|jacobi]
 
-N > 1 (torchrun, one rank per GPU): the fine level is row-partitioned (config C4, Jacobi smoother).
+N > 1 (torchrun, one rank per GPU): the finest --part-levels levels (default 3) are row-partitioned (config C4,
+Jacobi smoother).
 `--impl reference` times the CPU restatement of the reference (oracle/, kind "port": the reference is
 pure Julia and no Julia runtime exists in the image) on the host cores; it is single-threaded
 because the reference's solve phase is (src/smoother.jl:73-90, README.md:120).
@@ -354,9 +355,8 @@ def run_ours(args):
     if world > 1:
         line["n1_same_workload"] = n1_same
         line["config"]["note"] = ("BASELINE config C4: Jacobi smoother (Gauss-Seidel, the N=1 headline config C3, is sequential over the "
-                                  "index range and does not shard); fine level split by rows, coarser levels on rank 0, so the whole-cycle "
-                                  "speed-up is Amdahl-bounded by the coarse levels (<= ~1.44x for 3-D RS); strong-scaling baseline = "
-                                  "n1_same_workload")
+                                  "index range and does not shard); the finest --part-levels levels are split by rows, the levels below them run "
+                                  "on rank 0, which bounds the whole-cycle speed-up (Amdahl); strong-scaling baseline = n1_same_workload")
         line["nccl_collectives_in_timed_region"] = None
     line.update(extra)
     print(json.dumps(line), flush=True)
