@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <memory>
 #include <string>
 #include <vector>
@@ -152,34 +153,49 @@ static HostCsr stage_csc_as_rows_of_transpose(const b200amg_csc_t* M) {
     const int64_t* cp = (const int64_t*)M->colptr;
     nnz = cp[M->n] - base;
     REQUIRE(nnz >= 0 && nnz < INT32_MAX, B200AMG_ERR_UNSUPPORTED, "nnz does not fit the int32 device index width");
+#pragma omp parallel for schedule(static)
     for (int64_t j = 0; j <= M->n; ++j) out.ptr[j] = (int)(cp[j] - base);
   } else {
     const int32_t* cp = (const int32_t*)M->colptr;
     nnz = cp[M->n] - base;
     REQUIRE(nnz >= 0, B200AMG_ERR_BAD_ARG, "negative nnz");
+#pragma omp parallel for schedule(static)
     for (int64_t j = 0; j <= M->n; ++j) out.ptr[j] = cp[j] - base;
   }
   REQUIRE(nnz == 0 || (M->rowval && M->nzval), B200AMG_ERR_BAD_ARG, "null rowval/nzval");
   out.idx.resize(nnz);
-  out.val.assign(M->nzval, M->nzval + nnz);
+  out.val.resize(nnz);
+  const double* nz = M->nzval;
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) out.val[k] = nz[k];
   if (M->index_bits == 64) {
     const int64_t* rv = (const int64_t*)M->rowval;
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < nnz; ++k) out.idx[k] = (int)(rv[k] - base);
   } else {
     const int32_t* rv = (const int32_t*)M->rowval;
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < nnz; ++k) out.idx[k] = rv[k] - base;
   }
-  for (int64_t j = 0; j < M->n; ++j) {
-    REQUIRE(out.ptr[j] <= out.ptr[j + 1], B200AMG_ERR_BAD_ARG, "colptr not monotone");
+  // validation (exceptions must not leave an OpenMP region: collect the first kind of violation, report after)
+  int bad = 0;
+  for (int64_t j = 0; j < M->n && !bad; ++j)
+    if (out.ptr[j] > out.ptr[j + 1] || out.ptr[j] < 0 || out.ptr[j + 1] > nnz) bad = 1;
+  REQUIRE(!bad && (M->n == 0 || out.ptr[0] == 0), B200AMG_ERR_BAD_ARG, "colptr not monotone");
+  const int64_t mrows = M->m;
+#pragma omp parallel for schedule(static) reduction(max : bad)
+  for (int64_t j = 0; j < M->n; ++j)
     for (int k = out.ptr[j]; k < out.ptr[j + 1]; ++k) {
-      REQUIRE(out.idx[k] >= 0 && out.idx[k] < M->m, B200AMG_ERR_BAD_ARG, "row index out of range");
-      REQUIRE(k == out.ptr[j] || out.idx[k - 1] < out.idx[k], B200AMG_ERR_BAD_ARG,
-              "row indices must be sorted and unique inside each column");
+      if (out.idx[k] < 0 || out.idx[k] >= mrows) bad = std::max(bad, 2);
+      else if (k != out.ptr[j] && out.idx[k - 1] >= out.idx[k]) bad = std::max(bad, 1);
     }
-  }
+  REQUIRE(bad != 2, B200AMG_ERR_BAD_ARG, "row index out of range");
+  REQUIRE(bad != 1, B200AMG_ERR_BAD_ARG, "row indices must be sorted and unique inside each column");
   return out;
 }
 
+// Entries land in their output row by an atomic cursor (any order), then every output row is sorted by index: the
+// result is the sequential counting-sort transpose (ascending input row inside an output row), built on all cores.
 static HostCsr transpose(const HostCsr& a) {
   HostCsr t;
   t.nrows = a.ncols;
@@ -188,21 +204,56 @@ static HostCsr transpose(const HostCsr& a) {
   t.ptr.assign(t.nrows + 1, 0);
   t.idx.resize(nnz);
   t.val.resize(nnz);
-  for (int64_t k = 0; k < nnz; ++k) t.ptr[a.idx[k] + 1]++;
+  int* cnt = t.ptr.data() + 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) __atomic_fetch_add(&cnt[a.idx[k]], 1, __ATOMIC_RELAXED);
   for (int64_t i = 0; i < t.nrows; ++i) t.ptr[i + 1] += t.ptr[i];
   std::vector<int> next(t.ptr.begin(), t.ptr.end() - 1);
+#pragma omp parallel for schedule(static)
   for (int64_t r = 0; r < a.nrows; ++r)
     for (int k = a.ptr[r]; k < a.ptr[r + 1]; ++k) {
-      const int q = next[a.idx[k]]++;
+      const int q = __atomic_fetch_add(&next[a.idx[k]], 1, __ATOMIC_RELAXED);
       t.idx[q] = (int)r;
       t.val[q] = a.val[k];
     }
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t i = 0; i < t.nrows; ++i) {   // insertion sort: rows are short and nearly sorted
+    const int b = t.ptr[i], e = t.ptr[i + 1];
+    for (int k = b + 1; k < e; ++k) {
+      const int ci = t.idx[k];
+      const double cv = t.val[k];
+      int j = k - 1;
+      while (j >= b && t.idx[j] > ci) { t.idx[j + 1] = t.idx[j]; t.val[j + 1] = t.val[j]; --j; }
+      t.idx[j + 1] = ci;
+      t.val[j + 1] = cv;
+    }
+  }
   return t;
 }
 
 static bool bit_equal(const HostCsr& a, const HostCsr& b) {
   return a.nrows == b.nrows && a.ncols == b.ncols && a.ptr == b.ptr && a.idx == b.idx &&
          std::memcmp(a.val.data(), b.val.data(), sizeof(double) * a.val.size()) == 0;
+}
+
+// 2: a equals its transpose bit for bit, 1: only the pattern is symmetric, 0: neither.  Every entry (i, j) looks its
+// mirror (j, i) up by binary search in row j (columns are sorted), rows in parallel: no transpose is materialised.
+static int symmetry_kind(const HostCsr& a) {
+  if (a.nrows != a.ncols) return 0;
+  int kind = 2;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(min : kind)
+  for (int64_t i = 0; i < a.nrows; ++i) {
+    if (kind == 0) continue;
+    for (int k = a.ptr[i]; k < a.ptr[i + 1]; ++k) {
+      const int j = a.idx[k];
+      const int* lo = a.idx.data() + a.ptr[j];
+      const int* hi = a.idx.data() + a.ptr[j + 1];
+      const int* it = std::lower_bound(lo, hi, (int)i);
+      if (it == hi || *it != (int)i) { kind = 0; break; }
+      if (std::memcmp(&a.val[it - a.idx.data()], &a.val[k], sizeof(double)) != 0) kind = std::min(kind, 1);
+    }
+  }
+  return kind;
 }
 
 // operator given as (stored CSC, adjoint flag) -> the operator compressed by ITS rows
@@ -256,6 +307,7 @@ static HostCsr permute_sym(const HostCsr& m, const HostPerm& p) {
     const int r = p.old_of_new[q];
     out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
   }
+#pragma omp parallel for schedule(static)
   for (int64_t q = 0; q < m.nrows; ++q) {
     const int r = p.old_of_new[q];
     int o = out.ptr[q];
@@ -278,6 +330,7 @@ static HostCsr permute_rows(const HostCsr& m, const HostPerm& p) {
     const int r = p.old_of_new[q];
     out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
   }
+#pragma omp parallel for schedule(static)
   for (int64_t q = 0; q < m.nrows; ++q) {
     const int r = p.old_of_new[q];
     std::copy(m.idx.begin() + m.ptr[r], m.idx.begin() + m.ptr[r + 1], out.idx.begin() + out.ptr[q]);
@@ -287,7 +340,9 @@ static HostCsr permute_rows(const HostCsr& m, const HostPerm& p) {
 }
 static void map_cols(HostCsr& m, const HostPerm& p) {
   if (p.identity()) return;
-  for (int& c : m.idx) c = p.new_of_old[c];
+  const int64_t nnz = (int64_t)m.idx.size();
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) m.idx[k] = p.new_of_old[m.idx[k]];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -310,6 +365,21 @@ static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v && *v ? atoi(v) : dflt;
 }
+// B200AMG_VERBOSE_UPLOAD=1: wall-clock of the host-side stages of add_level on stderr
+struct UploadTimer {
+  const char* what;
+  double t0;
+  bool on;
+  static double now() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+  }
+  explicit UploadTimer(const char* w) : what(w), t0(now()), on(env_int("B200AMG_VERBOSE_UPLOAD", 0) != 0) {}
+  ~UploadTimer() {
+    if (on) fprintf(stderr, "[b200amg] upload %-28s %8.3f s\n", what, now() - t0);
+  }
+};
 
 struct DevCsr {
   int64_t nrows = 0, ncols = 0, nnz = 0;
@@ -500,9 +570,13 @@ struct SmootherMatrix {
   void build(const HostCsr& hAt_in, int symmetry_, bool need_fwd, bool need_bwd, bool need_true_A) {
     symmetry = symmetry_;
     n = hAt_in.nrows;
-    HostCsr hA_in = transpose(hAt_in);
-    symmetric_bits = bit_equal(hA_in, hAt_in);
-    pattern_symmetric = symmetric_bits || (hA_in.ptr == hAt_in.ptr && hA_in.idx == hAt_in.idx);
+    int sym_kind;
+    { UploadTimer t("symmetry check"); sym_kind = symmetry_kind(hAt_in); }
+    symmetric_bits = sym_kind == 2;
+    pattern_symmetric = sym_kind >= 1;
+    HostCsr hA_own;                     // the true A by rows: only materialised when it differs from A'
+    if (!symmetric_bits) hA_own = transpose(hAt_in);
+    const HostCsr& hA_in = symmetric_bits ? hAt_in : hA_own;
     std::vector<int> lvlptr;
     HostCsr hAt_p, hA_p;
     const HostCsr* hAt = &hAt_in;
@@ -511,7 +585,9 @@ struct SmootherMatrix {
       const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
       const HostCsr& wt0 = symmetric_bits ? w0 : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA_in : hAt_in);
       int nlev = 0;
-      std::vector<int> level = wavefront_levels(w0, wt0, &nlev);
+      std::vector<int> level;
+      { UploadTimer t("wavefront levels"); level = wavefront_levels(w0, wt0, &nlev); }
+      UploadTimer t_perm("renumbering + permute");
       lvlptr.assign(nlev + 1, 0);
       for (int64_t i = 0; i < n; ++i) lvlptr[level[i] + 1]++;
       for (int l = 0; l < nlev; ++l) lvlptr[l + 1] += lvlptr[l];
@@ -534,6 +610,7 @@ struct SmootherMatrix {
     else if (need_true_A || symmetry == B200AMG_SYMMETRY_NONE) A.upload(*hA);
     const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA;
     std::vector<double> d(n, 0.0);
+#pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i)
       for (int k = w.ptr[i]; k < w.ptr[i + 1]; ++k)
         if (w.idx[k] == i) d[i] = w.val[k];
@@ -1848,16 +1925,18 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
   if (h->world > 1 && !fine_of_partition) finish_last_part_level(h);
   const bool remote = h->world > 1 && !fine_of_partition && h->rank != 0;   // the other levels live on rank 0 only
   {
-    HostCsr hP = stage_operator_by_rows(P);
-    HostCsr hR = stage_operator_by_rows(R);
+    HostCsr hP, hR;
+    { UploadTimer t("stage P, R by rows"); hP = stage_operator_by_rows(P); hR = stage_operator_by_rows(R); }
     REQUIRE(hP.nrows == L->n, B200AMG_ERR_DIM_MISMATCH, "P has %lld rows, A has %lld", (long long)hP.nrows, (long long)L->n);
     REQUIRE(hR.ncols == L->n, B200AMG_ERR_DIM_MISMATCH, "R has %lld columns, A has %lld", (long long)hR.ncols, (long long)L->n);
     REQUIRE(hR.nrows == hP.ncols, B200AMG_ERR_DIM_MISMATCH, "R has %lld rows but P has %lld columns", (long long)hR.nrows,
             (long long)hP.ncols);
     L->nc = hR.nrows;
     L->nnz_p = hP.nnz();
-    HostCsr hAt = stage_csc_as_rows_of_transpose(A);
+    HostCsr hAt;
+    { UploadTimer t("stage A"); hAt = stage_csc_as_rows_of_transpose(A); }
     L->nnz_a = hAt.nnz();
+    UploadTimer t_level("level total (after staging)");
     if (fine_of_partition) {
       L->remote = true;   // no full device copy of this level on any rank
       build_part_level(h, *L, hAt, hP, hR, symmetry);
