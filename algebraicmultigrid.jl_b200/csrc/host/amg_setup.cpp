@@ -79,19 +79,41 @@ int amgsetup_poisson(int ndim, const int64_t* dims, idx_t* colptr, idx_t* rowval
 // ---------------------------------------------------------------------------------------
 // transpose (copy(A')) for real matrices; output columns sorted.  m x n in, n x m out.
 // ---------------------------------------------------------------------------------------
+// Built on all cores: entries reach their output column through an atomic cursor (any order), then every
+// output column is sorted by index (columns are short) — the result is the sequential counting-sort
+// transpose, bit for bit.
 int amgsetup_transpose(int64_t m, int64_t n, const idx_t* colptr, const idx_t* rowval,
                        const double* nzval, idx_t* tcolptr, idx_t* trowval, double* tnzval) {
   const int64_t nnz = colptr[n];
   std::fill(tcolptr, tcolptr + m + 1, 0);
-  for (int64_t k = 0; k < nnz; ++k) tcolptr[rowval[k] + 1]++;
+  idx_t* cnt = tcolptr + 1;
+#pragma omp parallel for schedule(static)
+  for (int64_t k = 0; k < nnz; ++k) __atomic_fetch_add(&cnt[rowval[k]], 1, __ATOMIC_RELAXED);
   for (int64_t i = 0; i < m; ++i) tcolptr[i + 1] += tcolptr[i];
   std::vector<idx_t> next(tcolptr, tcolptr + m);
+#pragma omp parallel for schedule(static)
   for (int64_t j = 0; j < n; ++j)
     for (idx_t k = colptr[j]; k < colptr[j + 1]; ++k) {
-      idx_t q = next[rowval[k]]++;
+      const idx_t q = __atomic_fetch_add(&next[rowval[k]], 1, __ATOMIC_RELAXED);
       trowval[q] = (idx_t)j;
       if (nzval) tnzval[q] = nzval[k];
     }
+#pragma omp parallel for schedule(dynamic, 4096)
+  for (int64_t i = 0; i < m; ++i) {
+    const idx_t b = tcolptr[i], e = tcolptr[i + 1];
+    for (idx_t k = b + 1; k < e; ++k) {
+      const idx_t ci = trowval[k];
+      const double cv = nzval ? tnzval[k] : 0.0;
+      idx_t j = k - 1;
+      while (j >= b && trowval[j] > ci) {
+        trowval[j + 1] = trowval[j];
+        if (nzval) tnzval[j + 1] = tnzval[j];
+        --j;
+      }
+      trowval[j + 1] = ci;
+      if (nzval) tnzval[j + 1] = cv;
+    }
+  }
   return 0;
 }
 
