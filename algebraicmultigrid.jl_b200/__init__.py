@@ -9,6 +9,7 @@ There is no CPU fallback for the solve phase: without the CUDA library / a GPU t
 points raise.
 """
 from . import _hostlib
+from ._hostlib import set_galerkin_backend
 from .aggregate import StandardAggregation
 from .aggregation import JacobiProlongation, fit_candidates, smoothed_aggregation
 from .classical import direct_interpolation, ruge_stuben

@@ -30,7 +30,7 @@ SYMBOLS = [
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
-    "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child",
+    "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child", "b200amg_spgemm_begin", "b200amg_spgemm_fetch", "b200amg_spgemm_release",
 ]
 
 
@@ -91,6 +91,9 @@ def lib():
             "b200amg_residual": [vp, i32, vp, vp, vp, i32],
             "b200amg_coarse_solve": [vp, vp, vp, i32],
             "b200amg_norm": [vp, i64, vp, C.POINTER(dbl), i32],
+            "b200amg_spgemm_begin": [i32, i64, i64, i64, vp, vp, vp, vp, vp, vp, C.POINTER(i64)],
+            "b200amg_spgemm_fetch": [vp, vp, vp],
+            "b200amg_spgemm_release": [],
             "b200amg_pcg": [vp, vp, vp, i32, i32, dbl, dbl, vp, i32, C.POINTER(i32), C.POINTER(i32), i32],
             "b200amg_smoother_create": [C.POINTER(vp), i32, pcsc, psm, i32],
             "b200amg_smoother_apply": [vp, vp, vp, i32],
@@ -160,6 +163,26 @@ def partition_plan(level, rank, world, parent_level=None, parent_plan=None):
     out["halo_cols"] = out["halo_cols"][: nhalo.value].copy()
     out["send_idx"] = out["send_idx"][: nsend.value].copy()
     return out
+
+
+def spgemm(a, b, device=None):
+    """``a * b`` on the device (``b200amg_spgemm_begin`` / ``_fetch``): the Galerkin products of the setup phase, same
+    contract and bit-identical result as the host product ``_hostlib.spgemm`` (structural zeros kept)."""
+    from ._hostlib import _csc
+
+    if a.n != b.m:
+        raise ValueError(f"DimensionMismatch: {a.shape} * {b.shape}")
+    L = lib()
+    arrs = [np.ascontiguousarray(v, dtype=t) for v, t in ((a.colptr, np.int32), (a.rowval, np.int32), (a.nzval, np.float64),
+                                                          (b.colptr, np.int32), (b.rowval, np.int32), (b.nzval, np.float64))]
+    nnz = C.c_int64(0)
+    dev = _default_device() if device is None else device
+    _check(L.b200amg_spgemm_begin(dev, C.c_int64(a.m), C.c_int64(a.n), C.c_int64(b.n), *[_ptr(v) for v in arrs], C.byref(nnz)))
+    cp = np.empty(b.n + 1, np.int32)
+    cj = np.empty(nnz.value, np.int32)
+    cx = np.empty(nnz.value, np.float64)
+    _check(L.b200amg_spgemm_fetch(_ptr(cp), _ptr(cj), _ptr(cx)))
+    return _csc(a.m, b.n, cp, cj, cx)
 
 
 def _ptr(a):

@@ -161,8 +161,24 @@ def direct_interpolation(at, t, splitting):
     return _csc(int(nc.value), n, rp, rj, rx)
 
 
+_SPGEMM_BACKEND = os.environ.get("B200AMG_GALERKIN", "host")
+
+
+def set_galerkin_backend(name):
+    """Where the Galerkin products ``R*A`` and ``(R*A)*P`` of the setup phase run: ``"host"`` (OpenMP, the default) or
+    ``"device"`` (``b200amg_spgemm_*``, csrc/device/spgemm.cuh; bit-identical result, needs a GPU)."""
+    global _SPGEMM_BACKEND
+    if name not in ("host", "device"):
+        raise ValueError("galerkin backend must be 'host' or 'device'")
+    _SPGEMM_BACKEND = name
+
+
 def spgemm(a, b):
     """``a * b`` keeping structural zeros (Julia ``SparseArrays`` semantics)."""
+    if _SPGEMM_BACKEND == "device":
+        from . import _devlib
+
+        return _devlib.spgemm(a, b)
     if a.n != b.m:
         raise ValueError(f"DimensionMismatch: {a.shape} * {b.shape}")
     L = lib()

@@ -238,6 +238,18 @@ int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, in
 int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t backward, uint64_t* out, int64_t cap,
                                   int64_t* ntasks);
 /* the CUDA stream (cudaStream_t) every kernel of this handle is launched on */
+/* Setup phase, Galerkin products on the device: C = A * B for A (m x k) and B (k x n) given as
+ * compressed-sparse-column arrays with int32 0-based indices and sorted rows per column — the products `R*A` and
+ * `(R*A)*P` of `extend_hierarchy!` (src/classical.jl:46, src/aggregation.jl:145).  Semantics of the stdlib product the
+ * reference calls: sorted rows per column, structural zeros kept; the accumulation order per entry is the sequential
+ * column-by-column one, so the result is bit-identical to the host product.  _begin computes and returns nnz(C);
+ * _fetch copies colptr (n + 1), rowval and nzval (nnz) out and drops the pending result.  Not re-entrant.
+ * B200AMG_SPGEMM_SLOTS_M (environment, default 192): hash-table slots per batch of columns, in units of 2^20. */
+int32_t b200amg_spgemm_begin(int32_t device, int64_t m, int64_t k, int64_t n, const int32_t* Ap, const int32_t* Aj, const double* Ax,
+                             const int32_t* Bp, const int32_t* Bj, const double* Bx, int64_t* nnz_out);
+int32_t b200amg_spgemm_fetch(int32_t* Cp, int32_t* Cj, double* Cx);
+/* frees the hash-table scratch the products keep between calls (and any result not fetched) */
+int32_t b200amg_spgemm_release(void);
 int32_t b200amg_get_stream(b200amg_handle_t h, void** stream);
 /* raw device pointers of the level-0 work vectors (x, b) for zero-copy callers (torch / CUDA.jl) */
 int32_t b200amg_device_vectors(b200amg_handle_t h, double** x, double** b);

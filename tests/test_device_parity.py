@@ -541,3 +541,55 @@ def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence):
     assert np.linalg.norm(x - xr) / np.linalg.norm(xr) <= TOL_SOLVE_X
     assert dev.launch_count() > launches0
     ml.release()
+
+
+# ---- setup phase: Galerkin products on the device (csrc/device/spgemm.cuh) ----------------------
+def _same_csc(x, y):
+    return (x.shape == y.shape and np.array_equal(x.colptr, y.colptr) and np.array_equal(x.rowval, y.rowval)
+            and np.array_equal(x.nzval.view(np.int64), y.nzval.view(np.int64)))
+
+
+def test_device_galerkin_product_is_bit_identical_to_host(amg, fx, monkeypatch):
+    """`R*A` and `(R*A)*P` (classical.jl:46, aggregation.jl:145) through b200amg_spgemm_begin/_fetch: same pattern
+    (sorted rows, structural zeros kept) and the same bits as the host product; several batches when the scratch budget
+    is small; a hierarchy built with the device backend equals the host-built one level by level."""
+    from algebraicmultigrid_jl_b200 import _devlib, _hostlib
+
+    ml = amg.ruge_stuben(amg.poisson((16, 16, 16)))
+    sa = amg.smoothed_aggregation(amg.poisson((40, 40)))
+    pairs = []
+    for lv in ml.levels[:3]:
+        R = lv.R.materialize() if hasattr(lv.R, "materialize") else lv.R
+        P = lv.P.materialize() if hasattr(lv.P, "materialize") else lv.P
+        pairs += [(R, lv.A), (_hostlib.spgemm(R, lv.A), P)]
+    lv = sa.levels[0]
+    R = lv.R.materialize() if hasattr(lv.R, "materialize") else lv.R
+    P = lv.P.materialize() if hasattr(lv.P, "materialize") else lv.P
+    pairs += [(R, lv.A), (_hostlib.spgemm(R, lv.A), P)]
+    nons = fx.sprand_plus_diag(300, 0.03, 1.0, seed=5)
+    pairs += [(nons, nons), (nons, nons.transpose())]
+    # exact cancellation: a structural zero must be kept
+    import scipy.sparse as sp
+    a = amg.SparseMatrixCSC.from_scipy(sp.csc_matrix(np.array([[1.0, -1.0], [2.0, 3.0]])))
+    b = amg.SparseMatrixCSC.from_scipy(sp.csc_matrix(np.array([[1.0, 0.0], [1.0, 4.0]])))
+    pairs.append((a, b))
+    for budget in ("192", "1"):
+        monkeypatch.setenv("B200AMG_SPGEMM_SLOTS_M", budget)
+        for a_, b_ in pairs:
+            h = _hostlib.spgemm(a_, b_)
+            d = _devlib.spgemm(a_, b_)
+            assert _same_csc(h, d), (a_.shape, b_.shape, budget)
+    c = _devlib.spgemm(a, b)
+    assert c.nnz == 4 and 0.0 in list(c.nzval)          # (1)(1) + (-1)(1) = 0 stays stored
+    monkeypatch.delenv("B200AMG_SPGEMM_SLOTS_M")
+    try:
+        amg.set_galerkin_backend("device")
+        mld = amg.ruge_stuben(amg.poisson((16, 16, 16)))
+        sad = amg.smoothed_aggregation(amg.poisson((40, 40)))
+    finally:
+        amg.set_galerkin_backend("host")
+    for h_, d_ in ((ml, mld), (sa, sad)):
+        assert len(h_.levels) == len(d_.levels)
+        for lh, ld in zip(h_.levels, d_.levels):
+            assert _same_csc(lh.A, ld.A)
+        assert _same_csc(h_.final_A, d_.final_A)
