@@ -139,15 +139,32 @@ int amgsetup_is_bitsymmetric(int64_t n, const idx_t* colptr, const idx_t* rowval
 int64_t amgsetup_classical_strength(int64_t n, const idx_t* colptr, const idx_t* rowval,
                                     const double* nzval, double theta,
                                     idx_t* tcolptr, idx_t* trowval, double* tnzval) {
-  idx_t q = 0;
+  // pass 1 (all cores): how many entries of column i survive  (:21-32)
   tcolptr[0] = 0;
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
-    // find_max_off_diag  (strength.jl:39-49)
+    double mx = 0.0;   // find_max_off_diag  (strength.jl:39-49)
+    for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j)
+      if (rowval[j] != i) mx = std::max(mx, std::fabs(nzval[j]));
+    const double threshold = theta * mx;
+    idx_t kept = 0;
+    for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j) {
+      double v = nzval[j];
+      if (rowval[j] != i) v = (std::fabs(v) >= threshold) ? std::fabs(v) : 0.0;
+      if (v != 0.0) ++kept;
+    }
+    tcolptr[i + 1] = kept;
+  }
+  for (int64_t i = 0; i < n; ++i) tcolptr[i + 1] += tcolptr[i];
+  // pass 2 (all cores): fill and scale
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
     double mx = 0.0;
     for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j)
       if (rowval[j] != i) mx = std::max(mx, std::fabs(nzval[j]));
     const double threshold = theta * mx;
-    const idx_t q0 = q;
+    const idx_t q0 = tcolptr[i];
+    idx_t q = q0;
     for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j) {
       double v = nzval[j];
       if (rowval[j] != i) v = (std::fabs(v) >= threshold) ? std::fabs(v) : 0.0;   // :21-27
@@ -157,9 +174,8 @@ int64_t amgsetup_classical_strength(int64_t n, const idx_t* colptr, const idx_t*
     double m2 = 0.0;
     for (idx_t j = q0; j < q; ++j) m2 = std::max(m2, tnzval[j]);
     for (idx_t j = q0; j < q; ++j) tnzval[j] /= m2;
-    tcolptr[i + 1] = q;
   }
-  return q;
+  return tcolptr[n];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -320,7 +336,10 @@ int64_t amgsetup_direct_interpolation(int64_t n, const idx_t* Ap, const idx_t* A
   if (!Rj) return Rp[n];
   const double eps = std::numeric_limits<double>::epsilon();
   // value of At at (row, col i) for a T entry: T's pattern is a subset of At's, both sorted
+  int bad_pattern = 0;   // set (never cleared) by any thread that finds a T entry outside At's pattern
+#pragma omp parallel for schedule(static)
   for (int64_t i = 0; i < n; ++i) {
+    bool bad_row = false;
     if (splitting[i] == C_NODE) {
       Rj[Rp[i]] = (idx_t)i;
       Rx[Rp[i]] = 1.0;
@@ -332,12 +351,17 @@ int64_t amgsetup_direct_interpolation(int64_t n, const idx_t* Ap, const idx_t* A
       for (idx_t j = Tp[i]; j < Tp[i + 1]; ++j) {
         const idx_t row = Tj[j];
         while (a < Ap[i + 1] && Aj[a] != row) ++a;
-        if (a >= Ap[i + 1]) return -3;  // T's pattern must be a subset of At's
+        if (a >= Ap[i + 1]) { bad_row = true; break; }  // T's pattern must be a subset of At's
         const double sval = Ax[a];
         if (splitting[row] == C_NODE) {
           if (sval < 0) sum_strong_neg += sval; else sum_strong_pos += sval;
         }
       }
+    }
+    if (bad_row) {
+#pragma omp atomic write
+      bad_pattern = 1;
+      continue;
     }
     double sum_all_pos = 0, sum_all_neg = 0, diag = 0;
     for (idx_t j = Ap[i]; j < Ap[i + 1]; ++j) {
@@ -367,12 +391,14 @@ int64_t amgsetup_direct_interpolation(int64_t n, const idx_t* Ap, const idx_t* A
       }
     }
   }
+  if (bad_pattern) return -3;
   // coarse numbering = exclusive prefix sum of splitting  (classical.jl:180-186)
   std::vector<idx_t> map(n);
   idx_t sum = 0;
   for (int64_t i = 0; i < n; ++i) { map[i] = sum; sum += splitting[i]; }
   idx_t mx = -1;
   const int64_t nnz = Rp[n];
+#pragma omp parallel for schedule(static) reduction(max : mx)
   for (int64_t k = 0; k < nnz; ++k) { Rj[k] = map[Rj[k]]; mx = std::max(mx, Rj[k]); }
   *nc_out = (int64_t)mx + 1;
   return nnz;

@@ -47,6 +47,30 @@ def test_no_device_is_an_error_not_a_fallback(amg):
         raise AssertionError("the solve phase ran without a GPU")
 
 
+def test_device_galerkin_backend_has_no_cpu_fallback(amg):
+    """`set_galerkin_backend("device")` without a GPU must raise, never quietly use the host product."""
+    import pytest
+
+    from algebraicmultigrid_jl_b200 import _devlib
+
+    with pytest.raises(ValueError):
+        amg.set_galerkin_backend("cpu")
+    L = _devlib.lib()
+    assert L.b200amg_spgemm_fetch(None, None, None) == -5 or L.b200amg_spgemm_fetch(None, None, None) < 0   # nothing pending
+    assert L.b200amg_spgemm_release() == 0
+    if _devlib.device_count() > 0:
+        return
+    A = amg.poisson(50)
+    try:
+        amg.set_galerkin_backend("device")
+        with pytest.raises(_devlib.B200AmgError) as e:
+            amg.ruge_stuben(A)
+        assert e.value.code == -9
+    finally:
+        amg.set_galerkin_backend("host")
+    assert len(amg.ruge_stuben(A).levels) >= 1
+
+
 def test_null_and_state_errors(amg):
     from algebraicmultigrid_jl_b200 import _devlib
 
