@@ -984,6 +984,26 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
             xn[j] = __hiloint2double((int)mm[j].z, (int)mm[j].x);
             need &= ~(1u << j);
           }
+        if (need && poll_masked >= 2) {
+          // focused spin (poll_masked = 2; parity-tested, not yet timed on hardware): a full round is ~175 instructions per warp, which
+          // with 16 polling warps per SM is about as long as the L2 round trip itself; wait for ONE outstanding mailbox in
+          // a five-instruction loop instead, then let the next masked round collect whatever else has arrived meanwhile
+          const int jsel = __ffs((int)need) - 1;
+          int csel = c[0];
+#pragma unroll
+          for (int j = 1; j < kGsPrefetch; ++j) csel = (jsel == j) ? c[j] : csel;
+          const uint4* p = mail + csel;
+          uint4 q;
+          do {
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+            ++polls;
+          } while (q.y != e || q.w != e);
+          const double got = __hiloint2double((int)q.z, (int)q.x);
+#pragma unroll
+          for (int j = 0; j < kGsPrefetch; ++j)
+            if (jsel == j) xn[j] = got;
+          need &= ~(1u << jsel);
+        }
         if (need && poll_sleep) __nanosleep(poll_sleep);
       }
       if (stamp && rbase == 0) { stamp[3] = global_ns(); stamp[6] = polls; }
