@@ -132,4 +132,39 @@ function AlgebraicMultigrid.smooth!(x::Vector{Float64}, s::DeviceSmoother, b::Ve
     return nothing
 end
 
+"""
+    galerkin(R, A, P) -> R*A*P
+
+The Galerkin product of `extend_hierarchy!` (src/classical.jl:46, src/aggregation.jl:145) on the device
+(`b200amg_spgemm_begin` / `_fetch`): stdlib semantics (sorted rows per column, structural zeros kept) and the
+sequential accumulation order, so the result is bit-identical to `(R*A)*P` on the host.  The library takes 0-based
+`Int32` compressed-sparse-column arrays.
+"""
+function spgemm(A::SparseMatrixCSC{Float64,Int64}, B::SparseMatrixCSC{Float64,Int64}; device::Integer = 0)
+    size(A, 2) == size(B, 1) || throw(DimensionMismatch("A has $(size(A, 2)) columns, B has $(size(B, 1)) rows"))
+    ap, aj = Int32.(A.colptr .- 1), Int32.(A.rowval .- 1)
+    bp, bj = Int32.(B.colptr .- 1), Int32.(B.rowval .- 1)
+    nnzc = Ref{Int64}(0)
+    check(ccall((:b200amg_spgemm_begin, lib), Int32,
+                (Int32, Int64, Int64, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ref{Int64}),
+                device, size(A, 1), size(A, 2), size(B, 2), ap, aj, A.nzval, bp, bj, B.nzval, nnzc))
+    cp, cj, cx = Vector{Int32}(undef, size(B, 2) + 1), Vector{Int32}(undef, nnzc[]), Vector{Float64}(undef, nnzc[])
+    check(ccall((:b200amg_spgemm_fetch, lib), Int32, (Ptr{Int32}, Ptr{Int32}, Ptr{Float64}), cp, cj, cx))
+    return SparseMatrixCSC(size(A, 1), size(B, 2), Int64.(cp) .+ 1, Int64.(cj) .+ 1, cx)
+end
+galerkin(R, A, P) = spgemm(spgemm(R, A), P)
+
+"""
+    partition!(h, rank, world, nccl_id; levels = 1)
+
+One process per GPU (`b200amg_set_partition`): call on a fresh handle before the first `add_level`; `levels` finest
+levels are split by rows over the ranks (`B200AMG_OPT_PART_LEVELS` = option 12).  `nccl_id` is the 128-byte id rank 0
+obtained from `b200amg_nccl_unique_id` and broadcast by the host (MPI.jl, a file, ...).
+"""
+function partition!(h::Ptr{Cvoid}, rank::Integer, world::Integer, nccl_id::Vector{UInt8}; levels::Integer = 1)
+    check(ccall((:b200amg_set_partition, lib), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Int64), h, rank, world, nccl_id, length(nccl_id)))
+    levels == 1 || check(ccall((:b200amg_set_option, lib), Int32, (Ptr{Cvoid}, Int32, Float64), h, 12, Float64(levels)))
+    return h
+end
+
 end # module
