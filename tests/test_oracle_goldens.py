@@ -141,6 +141,19 @@ def test_cycles(amg):
             assert np.linalg.norm(b - A.matvec(x)) <= reltol * np.linalg.norm(b)
 
 
+def test_preconditioned_cg_grids(amg):
+    # test/runtests.jl:227-240 (LinearSolve `precs`: RS and SA preconditioned Krylov CG on three grids -> ones, rtol 1e-8);
+    # the Krylov solver is third-party there, here the oracle's PCG with the same preconditioner semantics (ldiv!: zero
+    # x, one cycle, preconditioner.jl:12-19)
+    for sz in ((10, 10), (20, 20), (50, 50)):
+        A = amg.poisson(sz)
+        u0 = np.ones(A.n)
+        b = A.matvec(u0)
+        for method in (amg.ruge_stuben, amg.smoothed_aggregation):
+            x = oracle.OracleHierarchy(method(A)).pcg(b, reltol=1e-10)
+            assert np.allclose(x, u0, rtol=1e-8, atol=0.0), (sz, method.__name__, np.abs(x - u0).max())
+
+
 def test_regression_56(amg):
     # test/test_regression.jl:59-69
     import scipy.sparse as sp
