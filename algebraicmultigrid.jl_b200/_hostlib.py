@@ -73,6 +73,8 @@ def _declare(L):
     L.amgsetup_sub.argtypes = [i64, i32p, i32p, f64p, i32p, i32p, f64p, i32p, i32p, f64p]
     L.amgsetup_gs_sweeps.restype = C.c_int
     L.amgsetup_gs_sweeps.argtypes = [i64, i32p, i32p, f64p, f64p, f64p, i64, C.c_int, C.c_int, C.c_int]
+    L.amgsetup_residual_allcores.restype = C.c_double
+    L.amgsetup_residual_allcores.argtypes = [i64, i32p, i32p, f64p, f64p, f64p, f64p, C.c_int]
     L.amgsetup_csc_matvec.restype = C.c_int
     L.amgsetup_csc_matvec.argtypes = [i64, i64, i32p, i32p, f64p, f64p, f64p]
 
@@ -190,6 +192,15 @@ def spgemm(a, b):
     cx = np.empty(nnz, np.float64)
     L.amgsetup_spgemm_fetch(cp, cj, cx)
     return _csc(a.m, b.n, cp, cj, cx)
+
+
+def residual_allcores(a, x, b, reps=5):
+    """``(r, seconds)``: ``r = b - a x`` on all host cores for a numerically symmetric ``a`` (columns walked as rows) —
+    a courtesy figure for bench.py, not reference behaviour (the reference's solve phase is single-threaded)."""
+    r = np.empty(a.n, np.float64)
+    sec = lib().amgsetup_residual_allcores(a.n, a.colptr, a.rowval, a.nzval, np.ascontiguousarray(x, dtype=np.float64),
+                                            np.ascontiguousarray(b, dtype=np.float64), r, int(reps))
+    return r, float(sec)
 
 
 def standard_aggregation(s):

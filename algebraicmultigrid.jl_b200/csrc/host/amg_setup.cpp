@@ -658,4 +658,25 @@ int amgsetup_csc_matvec(int64_t m, int64_t n, const idx_t* Ap, const idx_t* Aj, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// r = b - A x on ALL host cores, walking the columns of a (numerically symmetric) CSC matrix as rows.  NOT reference
+// behaviour (the reference's solve phase is single-threaded): bench.py reports it as a courtesy upper bound of what the
+// host's memory system can do on the headline kernel.  Returns the best wall-clock seconds of `reps` passes.
+// ---------------------------------------------------------------------------------------
+double amgsetup_residual_allcores(int64_t n, const idx_t* ptr, const idx_t* idx, const double* val, const double* x,
+                                  const double* b, double* r, int reps) {
+  double best = 1e300;
+  for (int rep = 0; rep < (reps > 0 ? reps : 1); ++rep) {
+    const double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (idx_t k = ptr[i]; k < ptr[i + 1]; ++k) s += val[k] * x[idx[k]];
+      r[i] = b[i] - s;
+    }
+    best = std::min(best, omp_get_wtime() - t0);
+  }
+  return best;
+}
+
 }  // extern "C"

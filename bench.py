@@ -342,6 +342,16 @@ def run_ours(args):
         cpu = {"value": s / dt, "unit": "V-cycles/s", "cores": 1, "kind": "port",
                "sample": f"{s} `_solve!` iterations of the same hierarchy after 1 warm-up iteration, single thread "
                          f"(reference solve phase is single-threaded); host has {os.cpu_count()} logical cores"}
+        # courtesy figure, NOT reference behaviour (its solve phase is single-threaded): the headline kernel r = b - A x on all
+        # host cores (OpenMP over rows, host setup library), i.e. what the host's memory system can do on the same bytes
+        try:
+            from algebraicmultigrid_jl_b200 import _hostlib
+
+            _, sec = _hostlib.residual_allcores(A, xo, b, reps=5)
+            cpu["fine_residual_all_cores"] = {"ms": 1e3 * sec, "GBs": bytes_residual(n, nnz) / sec / 1e9, "threads": os.cpu_count(),
+                                              "note": "OpenMP row-parallel residual on all host cores; not reference behaviour"}
+        except Exception as exc:  # never let a courtesy figure break the bench line
+            cpu["fine_residual_all_cores"] = {"error": str(exc)[:200]}
         # parity of the timed run against the oracle after the same number of iterations is checked in tests/
     line = {
         "metric": "V-cycle iterations/s", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": K, "warmup": W,
