@@ -27,6 +27,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank; the host-side setup and upload (OpenMP) would then run on one core.
+# Give each rank its share of the host cores instead (before any OpenMP runtime is loaded).
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if _world > 1 and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
 import numpy as np  # noqa: E402
 
 SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
