@@ -61,6 +61,8 @@ def _declare(L):
     L.amgsetup_direct_interpolation.argtypes = [i64, i32p, i32p, f64p, i32p, i32p, i32p, i32p, C.c_void_p, C.c_void_p, C.POINTER(i64)]
     L.amgsetup_spgemm_begin.restype = i64
     L.amgsetup_spgemm_begin.argtypes = [i64, i64, i64, i32p, i32p, f64p, i32p, i32p, f64p]
+    L.amgsetup_spgemm_release.restype = None
+    L.amgsetup_spgemm_release.argtypes = []
     L.amgsetup_spgemm_fetch.restype = C.c_int
     L.amgsetup_spgemm_fetch.argtypes = [i32p, i32p, f64p]
     L.amgsetup_standard_aggregation.restype = i64
@@ -201,6 +203,11 @@ def residual_allcores(a, x, b, reps=5):
     sec = lib().amgsetup_residual_allcores(a.n, a.colptr, a.rowval, a.nzval, np.ascontiguousarray(x, dtype=np.float64),
                                             np.ascontiguousarray(b, dtype=np.float64), r, int(reps))
     return r, float(sec)
+
+
+def spgemm_release():
+    """Free the per-thread accumulators the host product keeps between calls (end of a setup)."""
+    lib().amgsetup_spgemm_release()
 
 
 def standard_aggregation(s):

@@ -71,6 +71,7 @@ def smoothed_aggregation(A, bs=1, *, B=None, symmetry=None, strength=None, aggre
         coarse_x_(w, A.m)
         coarse_b_(w, A.m)
         residual_(w, A.m)
+    _hostlib.spgemm_release()
     cs = coarse_solver(A)
     ml = MultiLevel(levels, A, cs, presmoother, postsmoother, w)
     if verbose:

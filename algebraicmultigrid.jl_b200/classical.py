@@ -38,6 +38,7 @@ def ruge_stuben(A, bs=1, *, strength=None, symmetry=None, CF=None, presmoother=N
         coarse_x_(w, A.m)
         coarse_b_(w, A.m)
         residual_(w, A.m)
+    _hostlib.spgemm_release()
     cs = coarse_solver(A)
     return MultiLevel(levels, A, cs, presmoother, postsmoother, w)
 

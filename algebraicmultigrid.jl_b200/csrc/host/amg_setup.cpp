@@ -419,6 +419,19 @@ struct SpgemmResult {
   int64_t n = 0, nnz = 0;
 };
 static SpgemmResult* g_spgemm = nullptr;
+static thread_local std::vector<double> tl_spgemm_acc;
+static thread_local std::vector<int64_t> tl_spgemm_mark;
+static thread_local int64_t tl_spgemm_stamp = 0;
+
+// gives the per-thread accumulators back (call when a hierarchy is finished; the OpenMP pool threads persist)
+void amgsetup_spgemm_release(void) {
+#pragma omp parallel
+  {
+    std::vector<double>().swap(tl_spgemm_acc);
+    std::vector<int64_t>().swap(tl_spgemm_mark);
+    tl_spgemm_stamp = 0;
+  }
+}
 
 int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, const idx_t* Aj,
                               const double* Ax, const idx_t* Bp, const idx_t* Bj, const double* Bx) {
@@ -442,8 +455,14 @@ int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, 
 #endif
     // contiguous static chunk of columns per thread so chunks concatenate in order
     const int64_t c0 = n * t / nthreads, c1 = n * (t + 1) / nthreads;
-    std::vector<double> acc(m, 0.0);
-    std::vector<idx_t> mark(m, -1);
+    // dense accumulator + marker per thread, kept between calls (a setup multiplies 2 x levels times): the marker
+    // holds "column + stamp" so nothing has to be cleared; only growth allocates
+    std::vector<double>& acc = tl_spgemm_acc;
+    std::vector<int64_t>& mark = tl_spgemm_mark;
+    int64_t& stamp = tl_spgemm_stamp;
+    if ((int64_t)acc.size() < m) { acc.resize(m); mark.assign(m, -1); stamp = 0; }
+    const int64_t base = stamp;          // marks of this call live in [base, base + n)
+    stamp += n + 1;
     std::vector<idx_t> list;
     std::vector<idx_t>& out_r = R.rows[t];
     std::vector<double>& out_v = R.vals[t];
@@ -455,7 +474,7 @@ int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, 
         for (idx_t ap = Ap[kk]; ap < Ap[kk + 1]; ++ap) {
           const idx_t r = Aj[ap];
           const double prod = Ax[ap] * bv;
-          if (mark[r] != (idx_t)j) { mark[r] = (idx_t)j; acc[r] = prod; list.push_back(r); }
+          if (mark[r] != base + j) { mark[r] = base + j; acc[r] = prod; list.push_back(r); }
           else acc[r] += prod;
         }
       }
