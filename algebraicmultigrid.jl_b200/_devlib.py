@@ -31,6 +31,7 @@ SYMBOLS = [
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
     "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child", "b200amg_spgemm_begin", "b200amg_spgemm_fetch", "b200amg_spgemm_release",
+    "b200amg_block_plan_check",
 ]
 
 
@@ -112,6 +113,7 @@ def lib():
             "b200amg_partition_plan_child": [pcsc, pcsc, pcsc, pcsc, vp, vp, i32, i32, vp, vp, vp, C.POINTER(i64), vp, vp, C.POINTER(i64),
                                              vp, vp, vp, i64],
             "b200amg_debug_gs_timeline": [vp, i32, i32, vp, i64, C.POINTER(i64)],
+            "b200amg_block_plan_check": [pcsc, vp, vp, vp, vp, vp, vp, dbl, i32, i32, C.c_char_p, i64],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -217,6 +219,34 @@ def csc_desc(op, keep):
     d.index_base = 0
     d.adjoint = adj
     return d
+
+
+BLOCK_STATS = ("ok", "tiles", "stages", "steps", "lanes", "wavefronts", "mean_step_rows_x1000", "theta", "a", "b", "max_tile_rows",
+               "max_tile_steps", "req_fwd", "req_bwd", "k_extent", "j_extent")
+
+
+def block_plan_check(A, x=None, b=None, omega=1.0, sor=False, sweep=3, tile_rows=0, block_a=0, block_b=0, stage_nnz=0, stage_rows=0,
+                     window=0, depth=0, verbose=0):
+    """Host-only: build + validate the blocked Gauss-Seidel plan of ``A`` (``b200amg_block_plan_check``) and, when ``x`` and ``b``
+    are given, run the host emulation of the kernel's sweep.  Returns ``(stats, message, new_of_old, x_out)``."""
+    import numpy as np
+
+    keep = []
+    d = csc_desc(A, keep)
+    params = np.array([tile_rows, block_a, block_b, stage_nnz, stage_rows, window, depth, verbose], dtype=np.int64)
+    stats = np.zeros(16, dtype=np.int64)
+    perm = np.zeros(A.n, dtype=np.int32)
+    msg = C.create_string_buffer(512)
+    xo = None
+    xp = bp = None
+    if x is not None:
+        xp = np.ascontiguousarray(x, dtype=np.float64)
+        bp = np.ascontiguousarray(b, dtype=np.float64)
+        xo = np.zeros(A.n)
+    _check(lib().b200amg_block_plan_check(C.byref(d), params.ctypes.data, stats.ctypes.data, perm.ctypes.data,
+                                          xp.ctypes.data if xp is not None else None, bp.ctypes.data if bp is not None else None,
+                                          xo.ctypes.data if xo is not None else None, float(omega), int(bool(sor)), int(sweep), msg, 512))
+    return dict(zip(BLOCK_STATS, stats.tolist())), msg.value.decode(errors="replace"), perm, xo
 
 
 def smoother_desc(config):

@@ -22,9 +22,12 @@
 #include "b200amg.h"
 #include "kernels.cuh"
 #include "stream.cuh"
+#include "host_csr.h"
 #include "partition.h"
 #include "cluster_gs.cuh"
 #include "dsm_gs.cuh"
+#include "block_plan.h"
+#include "block_gs.cuh"
 #include "spgemm.cuh"
 
 using namespace b200amg;
@@ -128,15 +131,6 @@ static NcclApi& nccl_api() {
     }                                                                                                      \
   } while (0)
 
-// ------------------------------------------------------------------------------------------
-// host-side sparse staging (int32, 0-based, "by rows" = compressed along the first index)
-// ------------------------------------------------------------------------------------------
-struct HostCsr {
-  int64_t nrows = 0, ncols = 0;
-  std::vector<int> ptr, idx;
-  std::vector<double> val;
-  int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
-};
 
 // The CSC arrays of an m x n matrix ARE the CSR arrays of its n x m transpose.
 static HostCsr stage_csc_as_rows_of_transpose(const b200amg_csc_t* M) {
@@ -195,67 +189,6 @@ static HostCsr stage_csc_as_rows_of_transpose(const b200amg_csc_t* M) {
   return out;
 }
 
-// Entries land in their output row by an atomic cursor (any order), then every output row is sorted by index: the
-// result is the sequential counting-sort transpose (ascending input row inside an output row), built on all cores.
-static HostCsr transpose(const HostCsr& a) {
-  HostCsr t;
-  t.nrows = a.ncols;
-  t.ncols = a.nrows;
-  const int64_t nnz = a.nnz();
-  t.ptr.assign(t.nrows + 1, 0);
-  t.idx.resize(nnz);
-  t.val.resize(nnz);
-  int* cnt = t.ptr.data() + 1;
-#pragma omp parallel for schedule(static)
-  for (int64_t k = 0; k < nnz; ++k) __atomic_fetch_add(&cnt[a.idx[k]], 1, __ATOMIC_RELAXED);
-  for (int64_t i = 0; i < t.nrows; ++i) t.ptr[i + 1] += t.ptr[i];
-  std::vector<int> next(t.ptr.begin(), t.ptr.end() - 1);
-#pragma omp parallel for schedule(static)
-  for (int64_t r = 0; r < a.nrows; ++r)
-    for (int k = a.ptr[r]; k < a.ptr[r + 1]; ++k) {
-      const int q = __atomic_fetch_add(&next[a.idx[k]], 1, __ATOMIC_RELAXED);
-      t.idx[q] = (int)r;
-      t.val[q] = a.val[k];
-    }
-#pragma omp parallel for schedule(dynamic, 4096)
-  for (int64_t i = 0; i < t.nrows; ++i) {   // insertion sort: rows are short and nearly sorted
-    const int b = t.ptr[i], e = t.ptr[i + 1];
-    for (int k = b + 1; k < e; ++k) {
-      const int ci = t.idx[k];
-      const double cv = t.val[k];
-      int j = k - 1;
-      while (j >= b && t.idx[j] > ci) { t.idx[j + 1] = t.idx[j]; t.val[j + 1] = t.val[j]; --j; }
-      t.idx[j + 1] = ci;
-      t.val[j + 1] = cv;
-    }
-  }
-  return t;
-}
-
-static bool bit_equal(const HostCsr& a, const HostCsr& b) {
-  return a.nrows == b.nrows && a.ncols == b.ncols && a.ptr == b.ptr && a.idx == b.idx &&
-         std::memcmp(a.val.data(), b.val.data(), sizeof(double) * a.val.size()) == 0;
-}
-
-// 2: a equals its transpose bit for bit, 1: only the pattern is symmetric, 0: neither.  Every entry (i, j) looks its
-// mirror (j, i) up by binary search in row j (columns are sorted), rows in parallel: no transpose is materialised.
-static int symmetry_kind(const HostCsr& a) {
-  if (a.nrows != a.ncols) return 0;
-  int kind = 2;
-#pragma omp parallel for schedule(dynamic, 4096) reduction(min : kind)
-  for (int64_t i = 0; i < a.nrows; ++i) {
-    if (kind == 0) continue;
-    for (int k = a.ptr[i]; k < a.ptr[i + 1]; ++k) {
-      const int j = a.idx[k];
-      const int* lo = a.idx.data() + a.ptr[j];
-      const int* hi = a.idx.data() + a.ptr[j + 1];
-      const int* it = std::lower_bound(lo, hi, (int)i);
-      if (it == hi || *it != (int)i) { kind = 0; break; }
-      if (std::memcmp(&a.val[it - a.idx.data()], &a.val[k], sizeof(double)) != 0) kind = std::min(kind, 1);
-    }
-  }
-  return kind;
-}
 
 // operator given as (stored CSC, adjoint flag) -> the operator compressed by ITS rows
 static HostCsr stage_operator_by_rows(const b200amg_csc_t* M) {
@@ -264,87 +197,6 @@ static HostCsr stage_operator_by_rows(const b200amg_csc_t* M) {
   return transpose(t);                            // operator == stored
 }
 
-// Wavefront (level) number of every row for an in-order FORWARD sweep over rows 0..n-1 of `a`, honouring
-// both true dependencies (a_ij, j earlier) and anti-dependencies (a_ji): the dependency graph is the
-// symmetrised pattern, which is why `at` (the transpose pattern) is needed.  The backward sweep walks
-// the same wavefronts in reverse order (level strictly increases along every edge, so the reversed
-// numbering is a valid schedule for the descending-index sweep).
-static std::vector<int> wavefront_levels(const HostCsr& a, const HostCsr& at, int* nlev_out) {
-  const int64_t n = a.nrows;
-  std::vector<int> level(n, 0);
-  int nlev = 0;
-  for (int64_t i = 0; i < n; ++i) {
-    int lv = 0;
-    for (int k = a.ptr[i]; k < a.ptr[i + 1]; ++k) {
-      const int j = a.idx[k];
-      if (j < i) lv = std::max(lv, level[j] + 1);
-    }
-    if (&at != &a)
-      for (int k = at.ptr[i]; k < at.ptr[i + 1]; ++k) {
-        const int j = at.idx[k];
-        if (j < i) lv = std::max(lv, level[j] + 1);
-      }
-    level[i] = lv;
-    nlev = std::max(nlev, lv + 1);
-  }
-  *nlev_out = nlev;
-  return level;
-}
-
-// A renumbering of one level: new index p holds old row old_of_new[p]; empty vectors = identity.
-struct HostPerm {
-  std::vector<int> new_of_old, old_of_new;
-  bool identity() const { return new_of_old.empty(); }
-};
-// rows AND columns renumbered; the order of the entries inside a row is kept (reference accumulation order)
-static HostCsr permute_sym(const HostCsr& m, const HostPerm& p) {
-  HostCsr out;
-  out.nrows = m.nrows; out.ncols = m.ncols;
-  out.ptr.resize(m.nrows + 1);
-  out.idx.resize(m.idx.size());
-  out.val.resize(m.val.size());
-  out.ptr[0] = 0;
-  for (int64_t q = 0; q < m.nrows; ++q) {
-    const int r = p.old_of_new[q];
-    out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
-  }
-#pragma omp parallel for schedule(static)
-  for (int64_t q = 0; q < m.nrows; ++q) {
-    const int r = p.old_of_new[q];
-    int o = out.ptr[q];
-    for (int k = m.ptr[r]; k < m.ptr[r + 1]; ++k, ++o) {
-      out.idx[o] = p.new_of_old[m.idx[k]];
-      out.val[o] = m.val[k];
-    }
-  }
-  return out;
-}
-static HostCsr permute_rows(const HostCsr& m, const HostPerm& p) {
-  if (p.identity()) return m;
-  HostCsr out;
-  out.nrows = m.nrows; out.ncols = m.ncols;
-  out.ptr.resize(m.nrows + 1);
-  out.idx.resize(m.idx.size());
-  out.val.resize(m.val.size());
-  out.ptr[0] = 0;
-  for (int64_t q = 0; q < m.nrows; ++q) {
-    const int r = p.old_of_new[q];
-    out.ptr[q + 1] = out.ptr[q] + (m.ptr[r + 1] - m.ptr[r]);
-  }
-#pragma omp parallel for schedule(static)
-  for (int64_t q = 0; q < m.nrows; ++q) {
-    const int r = p.old_of_new[q];
-    std::copy(m.idx.begin() + m.ptr[r], m.idx.begin() + m.ptr[r + 1], out.idx.begin() + out.ptr[q]);
-    std::copy(m.val.begin() + m.ptr[r], m.val.begin() + m.ptr[r + 1], out.val.begin() + out.ptr[q]);
-  }
-  return out;
-}
-static void map_cols(HostCsr& m, const HostPerm& p) {
-  if (p.identity()) return;
-  const int64_t nnz = (int64_t)m.idx.size();
-#pragma omp parallel for schedule(static)
-  for (int64_t k = 0; k < nnz; ++k) m.idx[k] = p.new_of_old[m.idx[k]];
-}
 
 // ------------------------------------------------------------------------------------------
 // device objects
@@ -537,6 +389,56 @@ static SmootherCfg to_cfg(const b200amg_smoother_t* s) {
   return c;
 }
 
+// Device copy of the blocked-sweep plan (block_plan.h / block_gs.cuh)
+struct DevBlockPlan {
+  bool ok = false;
+  int ntiles = 0, nstages = 0, lanes = 1, wavefronts = 0;
+  int4 *tile = nullptr, *stage_meta = nullptr, *stage_aux = nullptr;
+  int2 *stage_auxb = nullptr, *req_fwd = nullptr, *req_bwd = nullptr;
+  int* steps = nullptr;
+  unsigned* ctl = nullptr;   // [0] ticket, [kBgCtlProgress + t] published stages of tile t
+  size_t ctl_words = 0;
+  void upload(const BlockPlan& P) {
+    static_assert(sizeof(BI4) == sizeof(int4) && sizeof(BI2) == sizeof(int2), "plan records are uploaded as int4 / int2");
+    ntiles = P.ntiles; nstages = P.nstages; lanes = P.lanes; wavefronts = P.global_wavefronts;
+    auto up4 = [](const std::vector<BI4>& v) {
+      int4* p = dev_alloc<int4>((int64_t)v.size() + 2);
+      if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
+      return p;
+    };
+    auto up2 = [](const std::vector<BI2>& v) {
+      int2* p = dev_alloc<int2>((int64_t)v.size() + 2);
+      if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(int2) * v.size(), cudaMemcpyHostToDevice));
+      return p;
+    };
+    tile = up4(P.tile); stage_meta = up4(P.stage_meta); stage_aux = up4(P.stage_aux);
+    stage_auxb = up2(P.stage_auxb); req_fwd = up2(P.req_fwd); req_bwd = up2(P.req_bwd);
+    steps = dev_upload(P.steps, 8);
+    ctl_words = (size_t)kBgCtlProgress + (size_t)ntiles + 8;
+    ctl = dev_alloc<unsigned>((int64_t)ctl_words);
+    CUDA_OK(cudaMemset(ctl, 0, sizeof(unsigned) * ctl_words));
+    ok = true;
+  }
+  void release() {
+    cudaFree(tile); cudaFree(stage_meta); cudaFree(stage_aux); cudaFree(stage_auxb); cudaFree(req_fwd); cudaFree(req_bwd);
+    cudaFree(steps); cudaFree(ctl);
+    tile = stage_meta = stage_aux = nullptr; stage_auxb = req_fwd = req_bwd = nullptr; steps = nullptr; ctl = nullptr;
+    ok = false;
+  }
+};
+static BlockPlanParams block_params_from_env() {
+  BlockPlanParams prm;
+  prm.stage_nnz = kBgStageNnz; prm.stage_rows = kBgStageRows; prm.window = kBgWindow; prm.depth = kBgDepth;
+  prm.step_us = 1e-3 * env_int("B200AMG_BLOCK_STEP_NS", 220);
+  prm.cta_gbs = env_int("B200AMG_BLOCK_CTA_GBS", 55);
+  prm.force_tile_rows = env_int("B200AMG_BLOCK_TILE_ROWS", 0);
+  prm.force_a = env_int("B200AMG_BLOCK_A", 0);
+  prm.force_b = env_int("B200AMG_BLOCK_B", 0);
+  prm.max_lanes = 32;
+  prm.verbose = env_int("B200AMG_BLOCK_VERBOSE", 0);
+  return prm;
+}
+
 // A matrix prepared for relaxation: the rows the smoother walks + wavefront schedules + diagonal.
 // When a Gauss-Seidel / SOR sweep is requested the level is renumbered into wavefront order (perm).
 struct SmootherMatrix {
@@ -565,6 +467,7 @@ struct SmootherMatrix {
   int* dsm_status = nullptr;
   uint4* mail = nullptr;
   unsigned* mail_ctl = nullptr;
+  DevBlockPlan block;       // blocked sweep (block_gs.cuh): the default for structurally symmetric patterns
   const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
 
   // hAt_in: rows of A' (the staged CSC)
@@ -582,7 +485,33 @@ struct SmootherMatrix {
     HostCsr hAt_p, hA_p;
     const HostCsr* hAt = &hAt_in;
     const HostCsr* hA = &hA_in;
-    if ((need_fwd || need_bwd) && n > 0) {
+    bool blocked = false;
+    if ((need_fwd || need_bwd) && n > 0 && pattern_symmetric && env_int("B200AMG_GS_BLOCK", 1)) {
+      // blocked sweep: tiles of rows relaxed by one CTA each, rows renumbered (tile, local step, old index)
+      const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
+      BlockPlan plan;
+      { UploadTimer t("block plan"); plan = build_block_plan(w0, block_params_from_env()); }
+      if (plan.ok) {
+        UploadTimer t_perm("renumbering + permute");
+        perm = std::move(plan.perm);
+        hAt_p = permute_sym(hAt_in, perm);
+        hAt = &hAt_p;
+        if (!symmetric_bits) { hA_p = permute_sym(hA_in, perm); hA = &hA_p; } else hA = &hAt_p;
+        d_new_of_old = dev_upload(perm.new_of_old);
+        d_old_of_new = dev_upload(perm.old_of_new);
+        block.upload(plan);
+        nlev = plan.global_wavefronts;
+        blocked = true;
+        if (env_int("B200AMG_BLOCK_VERBOSE", 0))
+          fprintf(stderr, "[b200amg] block plan: n=%lld nnz=%lld wavefronts=%d lanes=%d tiles=%d stages=%d steps=%d rows/step %.1f (target %.1f) theta=%.0f a=%d b=%d max tile rows %lld steps %d\n",
+                  (long long)n, (long long)plan.nnz, plan.global_wavefronts, plan.lanes, plan.ntiles, plan.nstages, plan.nsteps,
+                  plan.mean_step_rows, plan.target_step_rows, plan.theta, plan.block_a, plan.block_b, (long long)plan.max_tile_rows,
+                  plan.max_tile_steps);
+      } else if (env_int("B200AMG_BLOCK_VERBOSE", 0)) {
+        fprintf(stderr, "[b200amg] block plan rejected (%s): wavefront sweeps\n", plan.why.c_str());
+      }
+    }
+    if ((need_fwd || need_bwd) && n > 0 && !blocked) {
       const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
       const HostCsr& wt0 = symmetric_bits ? w0 : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA_in : hAt_in);
       int nlev = 0;
@@ -627,6 +556,12 @@ struct SmootherMatrix {
       REQUIRE(bad < 0, B200AMG_ERR_SINGULAR, "SingularException(%lld)", (long long)(bad + 1));
     }
     const double mean = n ? (double)w.nnz() / (double)n : 0.0;
+    if (blocked) {   // the wavefront schedules of the other sweep kernels do not exist in this numbering
+      fwd.backward = 0; bwd.backward = 1;
+      fwd.nlev = bwd.nlev = nlev;
+      fwd.n = bwd.n = n;
+      return;
+    }
     if (need_fwd) fwd.upload(lvlptr, false, mean, walked().lanes);
     if (need_bwd) bwd.upload(lvlptr, true, mean, walked().lanes);
     if ((need_fwd || need_bwd) && n > 0) {
@@ -748,7 +683,7 @@ struct SmootherMatrix {
     }
   }
   void release() {
-    A.release(); At.release(); fwd.release(); bwd.release();
+    A.release(); At.release(); fwd.release(); bwd.release(); block.release();
     cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr); cudaFree(gs_meta); cudaFree(gs_tile_wave);
     cudaFree(dsm_meta); cudaFree(dsm_aux); cudaFree(dsm_status); cudaFree(dsm_code); cudaFree(dsm_rowof); cudaFree(dsm_own_off); cudaFree(dsm_wave_tiles);
     dsm_meta = nullptr; dsm_aux = nullptr; dsm_status = nullptr; dsm_code = dsm_rowof = dsm_own_off = dsm_wave_tiles = nullptr; dsm_ntiles = 0;
@@ -818,6 +753,7 @@ struct b200amg_hierarchy {
   Part* part = nullptr;                       // parts[0]: what solve / cycle / precond load and store
   int part_levels = 1;                        // how many of the finest levels are partitioned (world > 1)
   cudaStream_t stream = nullptr;
+  int num_sms = kNumSM;                       // queried at create
   std::vector<std::unique_ptr<Level>> levels;
   // coarsest
   bool have_coarse = false;
@@ -1248,6 +1184,36 @@ static bool launch_gs_dsm(H* h, const SmootherMatrix& M, const DevCsr& A, const 
     default: return false;
   }
 }
+// ---- blocked sweep (block_gs.cuh) ----
+template <int T>
+static void gs_block_set_attr() {
+  CUDA_OK(cudaFuncSetAttribute(gs_block_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBgSmemBytes));
+}
+static void gs_block_kernels_init() {
+  gs_block_set_attr<1>(); gs_block_set_attr<2>(); gs_block_set_attr<4>(); gs_block_set_attr<8>(); gs_block_set_attr<16>(); gs_block_set_attr<32>();
+}
+static void launch_gs_block(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
+                            int sor) {
+  const DevBlockPlan& B = M.block;
+  CUDA_OK(cudaMemsetAsync(B.ctl, 0, sizeof(unsigned) * B.ctl_words, h->stream));
+  const int ctas = std::min(B.ntiles, h->num_sms);
+  const int2* req = sc.backward ? B.req_bwd : B.req_fwd;
+#define B200AMG_BG_CASE(TT)                                                                                                       \
+  case TT:                                                                                                                        \
+    gs_block_kernel<TT><<<ctas, kBgThreads, kBgSmemBytes, h->stream>>>(B.ntiles, B.tile, B.stage_meta, B.stage_aux, B.stage_auxb, \
+                                                                      B.steps, req, B.ctl, A.ptr, A.idx, A.val, x, b, w, sor,   \
+                                                                      sc.backward, h->gs_debug);                                 \
+    break;
+  switch (B.lanes) {
+    B200AMG_BG_CASE(1) B200AMG_BG_CASE(2) B200AMG_BG_CASE(4) B200AMG_BG_CASE(8) B200AMG_BG_CASE(16)
+    default:
+      gs_block_kernel<32><<<ctas, kBgThreads, kBgSmemBytes, h->stream>>>(B.ntiles, B.tile, B.stage_meta, B.stage_aux, B.stage_auxb, B.steps,
+                                                                        req, B.ctl, A.ptr, A.idx, A.val, x, b, w, sor, sc.backward,
+                                                                        h->gs_debug);
+  }
+#undef B200AMG_BG_CASE
+  count_launch(h);
+}
 constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
 template <int T, bool XS>
 static void gs_cta_set_attr() {
@@ -1289,6 +1255,7 @@ static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const 
 }
 static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   const DevCsr& A = M.walked();
+  if (M.block.ok) { launch_gs_block(h, M, A, sc, x, b, w, sor); return; }
   if (h->gs_mode >= 1 && h->gs_dsm && M.d_fwd_lvlptr && M.dsm_ntiles > 0 && M.dsm_log_nc <= h->gs_dsm_max_log_nc &&
       !(sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width)) {
     if (launch_gs_dsm(h, M, A, sc, x, b, w, sor)) return;
@@ -1822,6 +1789,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   stream_kernels_init();
   gs_cta_kernels_init();
   dsm_kernels_init();
+  gs_block_kernels_init();
+  CUDA_OK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   gs_tile_ctas<1>(); gs_tile_ctas<2>(); gs_tile_ctas<4>(); gs_tile_ctas<8>(); gs_tile_ctas<16>(); gs_tile_ctas<32>();
   h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
   h->gs_mode = env_int("B200AMG_GS_MODE", 2);
@@ -2093,6 +2062,57 @@ int32_t b200amg_partition_plan_child(const b200amg_csc_t* A, const b200amg_csc_t
   REQUIRE(parent_P, B200AMG_ERR_BAD_ARG, "null parent P");
   partition_plan_impl(A, P, R, parent_P, parent_row_split, parent_coarse_split, rank, world, row_split, coarse_split, halo_cols, nhalo,
                       recv_off, send_idx, nsend, send_off, cx_lo, cx_hi, cap);
+  API_END
+}
+
+// Host-only (no device needed): build the blocked Gauss-Seidel plan of a matrix (block_plan.h), check every invariant
+// the kernel relies on and, when x / b are given, run the host emulation of the kernel's sweep (same stage / step / window
+// / far-gather rules) so the CPU tests can compare it with the sequential sweep.
+int32_t b200amg_block_plan_check(const b200amg_csc_t* A, const int64_t* params, int64_t* stats, int32_t* new_of_old, const double* x,
+                                 const double* b, double* x_out, double omega, int32_t sor, int32_t sweep, char* msg, int64_t msg_cap) {
+  API_BEGIN
+  REQUIRE(A && stats, B200AMG_ERR_BAD_ARG, "null argument");
+  if (msg && msg_cap > 0) msg[0] = 0;
+  HostCsr w = stage_csc_as_rows_of_transpose(A);   // the rows the "fast" smoothers walk (smoother.jl:81-86)
+  REQUIRE(w.nrows == w.ncols, B200AMG_ERR_DIM_MISMATCH, "matrix must be square");
+  REQUIRE(symmetry_kind(w) >= 1, B200AMG_ERR_UNSUPPORTED, "the blocked sweep needs a structurally symmetric pattern");
+  BlockPlanParams prm = block_params_from_env();
+  if (params) {
+    if (params[0] > 0) prm.force_tile_rows = (int)params[0];
+    if (params[1] > 0) prm.force_a = (int)params[1];
+    if (params[2] > 0) prm.force_b = (int)params[2];
+    if (params[3] > 0) prm.stage_nnz = (int)params[3];
+    if (params[4] > 0) prm.stage_rows = (int)params[4];
+    if (params[5] > 0) prm.window = (int)params[5];
+    if (params[6] > 0) prm.depth = (int)params[6];
+    prm.verbose = (int)params[7];
+  }
+  BlockPlan P = build_block_plan(w, prm);
+  for (int q = 0; q < 16; ++q) stats[q] = 0;
+  stats[0] = P.ok;
+  if (!P.ok) {
+    if (msg && msg_cap > 0) snprintf(msg, (size_t)msg_cap, "%s", P.why.c_str());
+    return B200AMG_OK;
+  }
+  stats[1] = P.ntiles; stats[2] = P.nstages; stats[3] = P.nsteps; stats[4] = P.lanes; stats[5] = P.global_wavefronts;
+  stats[6] = (int64_t)(1000.0 * P.mean_step_rows); stats[7] = (int64_t)P.theta; stats[8] = P.block_a; stats[9] = P.block_b;
+  stats[10] = P.max_tile_rows; stats[11] = P.max_tile_steps; stats[12] = (int64_t)P.req_fwd.size(); stats[13] = (int64_t)P.req_bwd.size();
+  stats[14] = P.k_extent; stats[15] = P.j_extent;
+  HostCsr wp = permute_sym(w, P.perm);
+  const std::string err = validate_block_plan(P, wp);
+  if (!err.empty()) {
+    stats[0] = -1;
+    if (msg && msg_cap > 0) snprintf(msg, (size_t)msg_cap, "%s", err.c_str());
+  }
+  if (new_of_old) std::copy(P.perm.new_of_old.begin(), P.perm.new_of_old.end(), new_of_old);
+  if (x && b && x_out) {
+    const int64_t n = w.nrows;
+    std::vector<double> xp((size_t)n), bp((size_t)n);
+    for (int64_t q = 0; q < n; ++q) { xp[q] = x[P.perm.old_of_new[q]]; bp[q] = b[P.perm.old_of_new[q]]; }
+    if (sweep == 1 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, false);
+    if (sweep == 2 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, true);
+    for (int64_t q = 0; q < n; ++q) x_out[P.perm.old_of_new[q]] = xp[q];
+  }
   API_END
 }
 
@@ -2478,7 +2498,7 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
     if (n) *n = L.n;
     if (nnz_a) *nnz_a = L.nnz_a;
     if (nnz_p) *nnz_p = L.nnz_p;
-    if (wavefronts) *wavefronts = L.M.fwd.built ? L.M.fwd.nlev : (L.M.bwd.built ? L.M.bwd.nlev : 0);
+    if (wavefronts) *wavefronts = L.M.block.ok ? L.M.block.wavefronts : (L.M.fwd.built ? L.M.fwd.nlev : (L.M.bwd.built ? L.M.bwd.nlev : 0));
   }
   API_END
 }
@@ -2623,6 +2643,22 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
   REQUIRE(level >= 0 && level < (int)h->levels.size() && out && ntasks, B200AMG_ERR_BAD_ARG, "bad argument");
   Level& L = *h->levels[level];
   const DevSchedule& sc = backward ? L.M.bwd : L.M.fwd;
+  if (L.M.block.ok) {   // blocked sweep: 8 words per tile (block_gs.cuh)
+    const int64_t words = (int64_t)L.M.block.ntiles * 8;
+    REQUIRE(cap >= words, B200AMG_ERR_BAD_ARG, "timeline buffer too small (%lld needed)", (long long)words);
+    unsigned long long* d = dev_alloc<unsigned long long>(words);
+    CUDA_OK(cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)words, h->stream));
+    h->gs_debug = d;
+    double* xb = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
+    const double* bb = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
+    launch_gs_block(h, L.M, L.M.walked(), sc, xb, bb, L.pre.omega, L.pre.kind == B200AMG_SMOOTHER_SOR);
+    h->gs_debug = nullptr;
+    CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    *ntasks = L.M.block.ntiles;
+    return B200AMG_OK;
+  }
   REQUIRE(sc.built, B200AMG_ERR_STATE, "no Gauss-Seidel schedule on this level");
   const bool wide = sc.nlev > 0 && L.M.n / sc.nlev >= h->gs_mail_min_width;
   const bool dsm = !wide && h->gs_dsm && L.M.dsm_ntiles > 0 && L.M.dsm_log_nc <= h->gs_dsm_max_log_nc;   // 8 stamps per tile (dsm_gs.cuh)

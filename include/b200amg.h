@@ -140,6 +140,17 @@ int32_t b200amg_partition_plan_child(const b200amg_csc_t* A, const b200amg_csc_t
                                      const int64_t* parent_row_split, const int64_t* parent_coarse_split, int32_t rank, int32_t world,
                                      int64_t* row_split, int64_t* coarse_split, int32_t* halo_cols, int64_t* nhalo, int32_t* recv_off,
                                      int32_t* send_idx, int64_t* nsend, int32_t* send_off, int64_t* cx_lo, int64_t* cx_hi, int64_t cap);
+/* Host-only (no device needed): the plan of the blocked exact-order Gauss-Seidel / SOR sweep for matrix A (structurally
+ * symmetric) — tiles, stages, local steps, cross-tile requirements (csrc/device/block_plan.h) — built, validated against
+ * every invariant the kernel relies on, and optionally EXECUTED by the host emulation of the kernel: x_out = the sweep(s)
+ * `sweep` (1 forward, 2 backward, 3 symmetric) applied to x with right-hand side b (all in the caller's numbering).
+ * params (may be NULL; 0 = default): [0] contiguous tile rows, [1] block a, [2] block b, [3] stage entries, [4] stage rows,
+ * [5] window, [6] depth, [7] verbose.  stats[16]: [0] 1 ok / 0 not applicable / -1 invariant violated (msg says which),
+ * [1] tiles, [2] stages, [3] steps, [4] lanes per row, [5] wavefronts of the whole level, [6] 1000 x mean rows per step,
+ * [7] theta, [8] a, [9] b, [10] rows of the largest tile, [11] steps of the longest tile, [12] / [13] forward / backward
+ * requirements, [14] / [15] extents of the K / J coordinates.  new_of_old (may be NULL): n entries. */
+int32_t b200amg_block_plan_check(const b200amg_csc_t* A, const int64_t* params, int64_t* stats, int32_t* new_of_old, const double* x,
+                                 const double* b, double* x_out, double omega, int32_t sor, int32_t sweep, char* msg, int64_t msg_cap);
 /* builds device layouts (row-major operators, transposes, wavefront schedules), workspaces and
  * the captured cycle graphs. */
 int32_t b200amg_finalize(b200amg_handle_t h);
