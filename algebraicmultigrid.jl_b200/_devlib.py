@@ -206,17 +206,26 @@ def _memkind(a):
     return MEM_DEVICE
 
 
-def csc_desc(op, keep):
-    """``b200amg_csc_t`` for a ``SparseMatrixCSC`` or a lazy ``Adjoint`` of one."""
+def csc_desc(op, keep, julia_indices=False):
+    """``b200amg_csc_t`` for a ``SparseMatrixCSC`` or a lazy ``Adjoint`` of one.  ``julia_indices``: hand the arrays over the way a
+    Julia caller holds them — ``Int64``, 1-based (``SparseMatrixCSC{Float64,Int64}``, ``src/classical.jl:64-65``) — instead of
+    this package's own int32 / 0-based storage."""
     adj = 0
     if hasattr(op, "parent"):
         op, adj = op.parent, 1
     keep.append(op)
     d = CscDesc()
     d.m, d.n = op.m, op.n
-    d.colptr, d.rowval, d.nzval = op.colptr.ctypes.data, op.rowval.ctypes.data, op.nzval.ctypes.data
-    d.index_bits = op.colptr.dtype.itemsize * 8
-    d.index_base = 0
+    colptr, rowval = op.colptr, op.rowval
+    base = 0
+    if julia_indices:
+        colptr = np.ascontiguousarray(op.colptr, dtype=np.int64) + 1
+        rowval = np.ascontiguousarray(op.rowval, dtype=np.int64) + 1
+        keep += [colptr, rowval]
+        base = 1
+    d.colptr, d.rowval, d.nzval = colptr.ctypes.data, rowval.ctypes.data, op.nzval.ctypes.data
+    d.index_bits = colptr.dtype.itemsize * 8
+    d.index_base = base
     d.adjoint = adj
     return d
 
@@ -272,7 +281,7 @@ def _default_device():
 class DeviceHierarchy:
     """Device-resident hierarchy: the handle behind a host ``MultiLevel``."""
 
-    def __init__(self, ml, device=None, partition=None):
+    def __init__(self, ml, device=None, partition=None, julia_indices=False):
         L = lib()
         self._h = C.c_void_p()
         self.device = _default_device() if device is None else device
@@ -286,11 +295,12 @@ class DeviceHierarchy:
                 if len(partition) > 3 and partition[3] != 1:
                     _check(L.b200amg_set_option(self._h, 12, float(partition[3])))      # B200AMG_OPT_PART_LEVELS
             for lv in ml.levels:
-                a, p, r = csc_desc(lv.A, keep), csc_desc(lv.P, keep), csc_desc(lv.R, keep)
+                a, p, r = (csc_desc(lv.A, keep, julia_indices), csc_desc(lv.P, keep, julia_indices),
+                           csc_desc(lv.R, keep, julia_indices))
                 pre, post = smoother_desc(lv.presmoother.config), smoother_desc(lv.postsmoother.config)
                 sym = SYMMETRY[lv.presmoother.symmetry_name]
                 _check(L.b200amg_add_level(self._h, C.byref(a), C.byref(p), C.byref(r), C.byref(pre), C.byref(post), sym))
-            fa = csc_desc(ml.final_A, keep)
+            fa = csc_desc(ml.final_A, keep, julia_indices)
             inv = np.ascontiguousarray(np.asarray(ml.coarse_solver.dense_operator(), dtype=np.float64).reshape(-1, order="F"))
             _check(L.b200amg_set_coarse(self._h, C.byref(fa), ml.final_A.n, _ptr(inv)))
             _check(L.b200amg_finalize(self._h))
@@ -422,6 +432,7 @@ class DeviceSmoother:
         keep = []
         a = csc_desc(A, keep)
         cfg = smoother_desc(config)
+        self.n = A.n
         rc = L.b200amg_smoother_create(C.byref(self._s), _default_device() if device is None else device, C.byref(a),
                                        C.byref(cfg), SYMMETRY[symmetry_name])
         if rc == -3:
@@ -432,6 +443,22 @@ class DeviceSmoother:
         _check(rc)
 
     def apply(self, x, b):
+        """``smooth!(x, s, b)``.  A 2-D ``x`` / ``b`` (n x m, the reference's block right-hand sides) is relaxed column by
+        column, as ``smooth!`` itself does (``for col in 1:size(x, 2)``, ``src/smoother.jl:77,118,195``): the C entry point
+        takes ONE vector of n doubles, and a C-contiguous n x m buffer is not m vectors laid end to end."""
+        if np.ndim(x) == 2:
+            if np.ndim(b) != 2 or np.shape(b) != np.shape(x):
+                raise AssertionError("x and b must have the same shape")
+            if np.shape(x)[0] != self.n:
+                raise ValueError(f"x has {np.shape(x)[0]} rows, the smoother's matrix {self.n}")
+            for j in range(np.shape(x)[1]):
+                xj = np.ascontiguousarray(x[:, j], dtype=np.float64) if isinstance(x, np.ndarray) else x[:, j].contiguous()
+                bj = np.ascontiguousarray(b[:, j], dtype=np.float64) if isinstance(b, np.ndarray) else b[:, j].contiguous()
+                _check(lib().b200amg_smoother_apply(self._s, _ptr(xj), _ptr(bj), _memkind(xj)))
+                x[:, j] = xj
+            return x
+        if np.ndim(x) != 1 or np.shape(x)[0] != self.n or np.shape(b) != np.shape(x):
+            raise ValueError(f"x and b must be vectors of length {self.n} (or n x m blocks)")
         xd = x if not isinstance(x, np.ndarray) else np.ascontiguousarray(x, dtype=np.float64)
         bd = b if not isinstance(b, np.ndarray) else np.ascontiguousarray(b, dtype=np.float64)
         _check(lib().b200amg_smoother_apply(self._s, _ptr(xd), _ptr(bd), _memkind(xd)))

@@ -206,8 +206,13 @@ def residual_allcores(a, x, b, reps=5):
 
 
 def spgemm_release():
-    """Free the per-thread accumulators the host product keeps between calls (end of a setup)."""
+    """Free what the Galerkin products keep between calls (end of a setup): the per-thread accumulators of the host product
+    and, when the device backend was used, its hash-table scratch on the GPU (up to a few GB)."""
     lib().amgsetup_spgemm_release()
+    if _SPGEMM_BACKEND == "device":
+        from . import _devlib
+
+        _devlib.lib().b200amg_spgemm_release()
 
 
 def standard_aggregation(s):

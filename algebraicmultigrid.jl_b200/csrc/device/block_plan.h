@@ -47,6 +47,7 @@ struct BlockPlanParams {
   int max_lanes = 32;
   double step_us = 0.22;    // one local step (barrier + dependent arithmetic)
   double cta_gbs = 55.0;    // what one CTA streams while every SM is busy
+  int cap_step_to_stage = 1;
   int force_tile_rows = 0;  // > 0: contiguous tiles of this many rows (diagnostics)
   int force_a = 0, force_b = 0;   // > 0: block sizes of the monotone coordinates
   int verbose = 0;
@@ -66,6 +67,8 @@ struct BlockPlan {
   std::vector<int> steps;       // end row (exclusive) of every step, stages concatenated
   std::vector<BI2> req_fwd;     // {tile, stages of it that must be complete (counted in forward order)}
   std::vector<BI2> req_bwd;     // {tile, stages of it that must be complete (counted from its LAST stage)}
+  std::vector<int> order_fwd;   // ticket -> tile: a topological order of the tile graph that hands tiles out by the wavefront
+  std::vector<int> order_bwd;   // they start with (there are more tiles than SMs: the resident ones must be the EARLIEST ones)
   // statistics
   double theta = 0, mean_step_rows = 0, target_step_rows = 0;
   int k_extent = 0, j_extent = 0, block_a = 0, block_b = 0, max_tile_steps = 0, global_wavefronts = 0;
@@ -150,7 +153,10 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
   const int D = global_wavefronts(w, glev);
   P.global_wavefronts = D;
   const double bytes_row = 12.0 * mean + 28.0;
-  const double X = std::min(256.0, std::max(8.0, prm.step_us * prm.cta_gbs * 1e3 / bytes_row));
+  // rows per step one CTA can stream in one step time — but a step should fit ONE pipeline stage (a split step costs a
+  // second hand-off)
+  const double xcap = prm.cap_step_to_stage ? std::min(0.75 * prm.stage_nnz / std::max(mean, 1.0), 0.75 * prm.stage_rows) : 1e9;
+  const double X = std::max(4.0, std::min(xcap, prm.step_us * prm.cta_gbs * 1e3 / bytes_row));
   P.target_step_rows = X;
 
   // ---- tiles -----------------------------------------------------------------------------------
@@ -183,7 +189,7 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
     if (P.k_extent < 4) theta = P.theta = 0.0;   // no third dimension to speak of: contiguous ranges
   }
   std::vector<int> step((size_t)n, 0);
-  std::vector<int> tile_rows_cnt, tile_nsteps;
+  std::vector<int> tile_rows_cnt, tile_nsteps, tmin, tmax;   // per tile: rows, steps, first / last wavefront of the level it holds
   int64_t a = 0, b = 0, trows = 0;
   if (theta > 0.0) {
     b = prm.force_b > 0 ? prm.force_b : std::max<int64_t>(1, (int64_t)std::llround(std::sqrt(X)));
@@ -218,7 +224,8 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
     // the neighbouring tile).
     tile_nsteps.assign((size_t)ntiles, 0);
     tile_rows_cnt.assign((size_t)ntiles, 0);
-    std::vector<int> tmin((size_t)ntiles, INT_MAX), tmax((size_t)ntiles, -1);
+    tmin.assign((size_t)ntiles, INT_MAX);
+    tmax.assign((size_t)ntiles, -1);
     for (int64_t i = 0; i < n; ++i) {
       const int t = tile_of[i];
       tmin[t] = std::min(tmin[t], glev[i]);
@@ -401,6 +408,38 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
       for (int q = 0; q < P.stage_auxb[g].y; ++q) P.req_bwd.push_back(rb[t][o++]);
     }
   }
+  // ---- ticket order: Kahn's algorithm with a priority queue keyed by the tile's first (forward) / last (backward) wavefront ----
+  {
+    auto topo = [&](const std::vector<std::vector<BI2>>& reqs, bool fwd, std::vector<int>& order) {
+      std::vector<std::vector<int>> succ((size_t)ntiles);
+      std::vector<int> indeg((size_t)ntiles, 0);
+      for (int t = 0; t < ntiles; ++t) {
+        std::vector<int> preds;
+        for (const BI2& r : reqs[t]) preds.push_back(r.x);
+        std::sort(preds.begin(), preds.end());
+        preds.erase(std::unique(preds.begin(), preds.end()), preds.end());
+        for (int pt : preds) { succ[(size_t)pt].push_back(t); indeg[t]++; }
+      }
+      auto key = [&](int t) { return fwd ? (int64_t)tmin[t] * ntiles + t : (int64_t)(D - tmax[t]) * ntiles + (ntiles - 1 - t); };
+      std::vector<std::pair<int64_t, int>> heap;
+      auto cmp = [](const std::pair<int64_t, int>& x, const std::pair<int64_t, int>& y) { return x.first > y.first; };
+      for (int t = 0; t < ntiles; ++t)
+        if (indeg[t] == 0) heap.push_back({key(t), t});
+      std::make_heap(heap.begin(), heap.end(), cmp);
+      order.clear();
+      while (!heap.empty()) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        const int t = heap.back().second;
+        heap.pop_back();
+        order.push_back(t);
+        for (int u : succ[(size_t)t])
+          if (--indeg[u] == 0) { heap.push_back({key(u), u}); std::push_heap(heap.begin(), heap.end(), cmp); }
+      }
+    };
+    topo(rf, true, P.order_fwd);
+    topo(rb, false, P.order_bwd);
+    if ((int)P.order_fwd.size() != ntiles || (int)P.order_bwd.size() != ntiles) { P.why = "internal: the tile graph has a cycle"; return P; }
+  }
   if (prm.verbose >= 2)
     for (int t = 0; t < std::min(ntiles, 24); ++t) {
       const int s0 = P.tile[t].x, s1 = P.tile[t].y;
@@ -415,6 +454,38 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
     }
   P.ok = true;
   return P;
+}
+
+// Per-entry codes of the walked matrix in its NEW numbering (`wp`), one array per sweep direction — everything about an entry
+// that does not change from sweep to sweep, so that the kernel's scout warps do not have to work it out again per stage:
+//   code >= 0                     FAR: the column index; the value of x is gathered from global memory when the stage is staged
+//   code = 0x80000000 | slot      NEAR: relaxed by the same tile at most window_eff rows earlier in the sweep; read from the
+//                                 shared-memory window, slot = column & (window - 1)
+//   code = 0xC0000000             the diagonal
+// dpos[row] = position of the row's diagonal in the value array (-1: none).
+constexpr int kBlockCodeNear = (int)0x80000000u, kBlockCodeDiag = (int)0xC0000000u;
+static inline void build_block_codes(const BlockPlan& P, const HostCsr& wp, std::vector<int>& code_fwd, std::vector<int>& code_bwd,
+                                     std::vector<int>& dpos) {
+  code_fwd.assign(wp.idx.size(), 0);
+  code_bwd.assign(wp.idx.size(), 0);
+  dpos.assign((size_t)P.n, -1);
+  const int W = P.window, WE = P.window_eff;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < P.ntiles; ++t) {
+    const int r0 = P.tile[t].z, r1 = P.tile[t].w;
+    for (int r = r0; r < r1; ++r)
+      for (int k = wp.ptr[r]; k < wp.ptr[r + 1]; ++k) {
+        const int c = wp.idx[k];
+        if (c == r) {
+          code_fwd[k] = code_bwd[k] = kBlockCodeDiag;
+          dpos[r] = k;
+          continue;
+        }
+        const bool in_tile = c >= r0 && c < r1;
+        code_fwd[k] = (in_tile && c < r && r - c <= WE) ? (kBlockCodeNear | (c & (W - 1))) : c;
+        code_bwd[k] = (in_tile && c > r && c - r <= WE) ? (kBlockCodeNear | (c & (W - 1))) : c;
+      }
+  }
 }
 
 // Checks every invariant the kernel relies on, against the matrix in its NEW numbering (`wp` = permute_sym(w, plan.perm)).
@@ -451,6 +522,13 @@ static inline std::string validate_block_plan(const BlockPlan& P, const HostCsr&
   if (prev_end != n) return "tiles do not cover the level";
   // requirements, replayed cumulatively per tile
   for (int dir = 0; dir < 2; ++dir) {
+    const std::vector<int>& order = dir == 0 ? P.order_fwd : P.order_bwd;
+    if ((int)order.size() != P.ntiles) return "ticket order is not a permutation of the tiles";
+    std::vector<int> ticket((size_t)P.ntiles, -1);
+    for (int q = 0; q < P.ntiles; ++q) {
+      if (order[q] < 0 || order[q] >= P.ntiles || ticket[order[q]] >= 0) return "ticket order is not a permutation of the tiles";
+      ticket[order[q]] = q;
+    }
     for (int t = 0; t < P.ntiles; ++t) {
       const BI4 T = P.tile[t];
       std::vector<BI2> have;
@@ -463,6 +541,7 @@ static inline std::string validate_block_plan(const BlockPlan& P, const HostCsr&
           const BI2 rq = req[(size_t)(rb + q)];
           if (rq.x < 0 || rq.x >= P.ntiles) return "requirement names a tile that does not exist";
           if (dir == 0 ? rq.x >= t : rq.x <= t) return "requirement on a tile that is not earlier in the sweep (cycle)";
+          if (ticket[rq.x] >= ticket[t]) return "requirement on a tile with a later ticket (the sweep could deadlock)";
           if (rq.y < 1 || rq.y > P.tile[rq.x].y - P.tile[rq.x].x) return "requirement count out of range";
           bool f = false;
           for (BI2& hq : have)
@@ -515,7 +594,7 @@ static inline void emulate_block_sweep(const BlockPlan& P, const HostCsr& wp, st
   const int W = P.window, W_EFF = P.window_eff;
   std::vector<double> win((size_t)W, 0.0), xs((size_t)P.stage_nnz + 8, 0.0);
   for (int tk = 0; tk < P.ntiles; ++tk) {
-    const int t = backward ? P.ntiles - 1 - tk : tk;
+    const int t = backward ? P.order_bwd[(size_t)tk] : P.order_fwd[(size_t)tk];
     const BI4 TT = P.tile[t];
     std::fill(win.begin(), win.end(), std::nan(""));   // nothing of another tile may be read from the window
     for (int i = 0; i < TT.y - TT.x; ++i) {

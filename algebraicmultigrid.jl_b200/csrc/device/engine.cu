@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges are no-ops unless a profiler is attached
 #include <nccl.h>   // types and prototypes only: the library is dlopen'ed when a partition is requested
 
 #include "b200amg.h"
@@ -396,6 +397,8 @@ struct DevBlockPlan {
   int4 *tile = nullptr, *stage_meta = nullptr, *stage_aux = nullptr;
   int2 *stage_auxb = nullptr, *req_fwd = nullptr, *req_bwd = nullptr;
   int* steps = nullptr;
+  int *order_fwd = nullptr, *order_bwd = nullptr;
+  int *code_fwd = nullptr, *code_bwd = nullptr, *dpos = nullptr;   // per-entry codes of the walked matrix (build_block_codes)
   unsigned* ctl = nullptr;   // [0] ticket, [kBgCtlProgress + t] published stages of tile t
   size_t ctl_words = 0;
   void upload(const BlockPlan& P) {
@@ -414,6 +417,8 @@ struct DevBlockPlan {
     tile = up4(P.tile); stage_meta = up4(P.stage_meta); stage_aux = up4(P.stage_aux);
     stage_auxb = up2(P.stage_auxb); req_fwd = up2(P.req_fwd); req_bwd = up2(P.req_bwd);
     steps = dev_upload(P.steps, 8);
+    order_fwd = dev_upload(P.order_fwd, 8);
+    order_bwd = dev_upload(P.order_bwd, 8);
     ctl_words = (size_t)kBgCtlProgress + (size_t)ntiles + 8;
     ctl = dev_alloc<unsigned>((int64_t)ctl_words);
     CUDA_OK(cudaMemset(ctl, 0, sizeof(unsigned) * ctl_words));
@@ -421,7 +426,8 @@ struct DevBlockPlan {
   }
   void release() {
     cudaFree(tile); cudaFree(stage_meta); cudaFree(stage_aux); cudaFree(stage_auxb); cudaFree(req_fwd); cudaFree(req_bwd);
-    cudaFree(steps); cudaFree(ctl);
+    cudaFree(steps); cudaFree(ctl); cudaFree(order_fwd); cudaFree(order_bwd); cudaFree(code_fwd); cudaFree(code_bwd); cudaFree(dpos);
+    order_fwd = order_bwd = code_fwd = code_bwd = dpos = nullptr;
     tile = stage_meta = stage_aux = nullptr; stage_auxb = req_fwd = req_bwd = nullptr; steps = nullptr; ctl = nullptr;
     ok = false;
   }
@@ -431,6 +437,7 @@ static BlockPlanParams block_params_from_env() {
   prm.stage_nnz = kBgStageNnz; prm.stage_rows = kBgStageRows; prm.window = kBgWindow; prm.depth = kBgDepth;
   prm.step_us = 1e-3 * env_int("B200AMG_BLOCK_STEP_NS", 220);
   prm.cta_gbs = env_int("B200AMG_BLOCK_CTA_GBS", 55);
+  prm.cap_step_to_stage = env_int("B200AMG_BLOCK_XCAP", 1);
   prm.force_tile_rows = env_int("B200AMG_BLOCK_TILE_ROWS", 0);
   prm.force_a = env_int("B200AMG_BLOCK_A", 0);
   prm.force_b = env_int("B200AMG_BLOCK_B", 0);
@@ -486,7 +493,15 @@ struct SmootherMatrix {
     const HostCsr* hAt = &hAt_in;
     const HostCsr* hA = &hA_in;
     bool blocked = false;
-    if ((need_fwd || need_bwd) && n > 0 && pattern_symmetric && env_int("B200AMG_GS_BLOCK", 1)) {
+    // Which exact-order sweep.  Measured on B200 (256^3 RS hierarchy, SGS ms, blocked vs wavefront kernels; profiles/
+    // r02_gs_block_vs_wavefront_256.log): stencil-like rows (7 entries, one lane per row) 3.54 vs 3.78, tiny levels (<= ~1000
+    // rows) 0.19 / 0.088 vs 0.22 / 0.093; on the irregular coarse levels in between (19-124 entries per row) the blocked
+    // sweep's per-stage pipeline latency loses (10.3 / 8.7 / 7.2 / 9.0 / 2.6 vs 7.8 / 6.3 / 5.0 / 6.2 / 2.2).
+    // B200AMG_GS_BLOCK: 0 never, 1 (default) by that rule, 2 always.
+    const int block_mode = env_int("B200AMG_GS_BLOCK", 1);
+    const double mean_row = n ? (double)hAt_in.nnz() / (double)n : 0.0;
+    const bool block_wanted = block_mode >= 2 || (block_mode == 1 && (mean_row <= 8.0 || n <= 1024));
+    if ((need_fwd || need_bwd) && n > 0 && pattern_symmetric && block_wanted) {
       // blocked sweep: tiles of rows relaxed by one CTA each, rows renumbered (tile, local step, old index)
       const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
       BlockPlan plan;
@@ -500,6 +515,14 @@ struct SmootherMatrix {
         d_new_of_old = dev_upload(perm.new_of_old);
         d_old_of_new = dev_upload(perm.old_of_new);
         block.upload(plan);
+        {
+          UploadTimer t_codes("block entry codes");
+          std::vector<int> cf, cb, dp;
+          build_block_codes(plan, symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA, cf, cb, dp);
+          block.code_fwd = dev_upload(cf, 8);
+          block.code_bwd = dev_upload(cb, 8);
+          block.dpos = dev_upload(dp, 8);
+        }
         nlev = plan.global_wavefronts;
         blocked = true;
         if (env_int("B200AMG_BLOCK_VERBOSE", 0))
@@ -776,6 +799,9 @@ struct b200amg_hierarchy {
   cudaGraphExec_t resnorm_graph = nullptr;
   bool use_graphs = true;
   bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
+  bool part_whole_graph = true;   // partitioned handles: the whole cycle (kernels + NCCL groups) is one captured graph per rank
+  cudaGraphExec_t part_cycle_graph[3] = {nullptr, nullptr, nullptr};
+  int64_t part_cycle_launches[3] = {0, 0, 0}, part_cycle_collectives[3] = {0, 0, 0};
   int stream_chunk = 4;   // consecutive tiles per CTA run of the stream kernels (0: contiguous split)
   int64_t gs_cta_rows = 12288;   // levels up to this many rows are swept by ONE CTA (bar.sync per wavefront, x in smem)
   int gs_cluster = 0;                 // one-cluster sweep (x in distributed shared memory) for mid-size levels: measured
@@ -797,6 +823,7 @@ struct b200amg_hierarchy {
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
   int gs_acquire = 0;     // consumer-side acquire of the dataflow sweep: 0 none (see stream.cuh), 1 ld.acquire, 2 fence
   unsigned long long* gs_debug = nullptr;   // 8 timestamps per task of the last dataflow sweep (diagnostics)
+  int* gs_fault = nullptr;                  // set by a sweep kernel whose watchdog fired (checked after every stream sync of an entry point)
   int gs_mode = 2;        // 2: per-row mailbox sweep (symmetric patterns; else 1), 1: wavefront-counter dataflow sweep,
                           // 0: one launch per wavefront (fallback / A-B)
   bool finalized = false;
@@ -1198,18 +1225,21 @@ static void launch_gs_block(H* h, const SmootherMatrix& M, const DevCsr& A, cons
   CUDA_OK(cudaMemsetAsync(B.ctl, 0, sizeof(unsigned) * B.ctl_words, h->stream));
   const int ctas = std::min(B.ntiles, h->num_sms);
   const int2* req = sc.backward ? B.req_bwd : B.req_fwd;
+  const int* order = sc.backward ? B.order_bwd : B.order_fwd;
+  const int* code = sc.backward ? B.code_bwd : B.code_fwd;
 #define B200AMG_BG_CASE(TT)                                                                                                       \
   case TT:                                                                                                                        \
     gs_block_kernel<TT><<<ctas, kBgThreads, kBgSmemBytes, h->stream>>>(B.ntiles, B.tile, B.stage_meta, B.stage_aux, B.stage_auxb, \
-                                                                      B.steps, req, B.ctl, A.ptr, A.idx, A.val, x, b, w, sor,   \
-                                                                      sc.backward, h->gs_debug);                                 \
+                                                                      B.steps, req, order, B.ctl, A.ptr, code, B.dpos, A.val, x, b, w, \
+                                                                      sor,                                                    \
+                                                                      sc.backward, h->gs_fault, h->gs_debug);                    \
     break;
   switch (B.lanes) {
     B200AMG_BG_CASE(1) B200AMG_BG_CASE(2) B200AMG_BG_CASE(4) B200AMG_BG_CASE(8) B200AMG_BG_CASE(16)
     default:
       gs_block_kernel<32><<<ctas, kBgThreads, kBgSmemBytes, h->stream>>>(B.ntiles, B.tile, B.stage_meta, B.stage_aux, B.stage_auxb, B.steps,
-                                                                        req, B.ctl, A.ptr, A.idx, A.val, x, b, w, sor, sc.backward,
-                                                                        h->gs_debug);
+                                                                        req, order, B.ctl, A.ptr, code, B.dpos, A.val, x, b, w, sor, sc.backward,
+                                                                        h->gs_fault, h->gs_debug);
   }
 #undef B200AMG_BG_CASE
   count_launch(h);
@@ -1345,11 +1375,18 @@ static void coarse_solve(H* h, double* x, const double* b) {
 // ------------------------------------------------------------------------------------------
 // the cycle: __solve!(x, ml, cycle, b, lvl)  — src/multilevel.jl:214-239, recursion :200-212
 // ------------------------------------------------------------------------------------------
+// The six sections the reference times with @timeit_debug (src/multilevel.jl:216-236), under the same names: an NVTX range
+// around the launches of every phase (nsys / ncu --nvtx line the device work up with the reference's timer labels; when the
+// cycle is replayed as a CUDA graph the ranges mark its capture), and CUDA-event timers for b200amg_profile_cycle.
+static const char* const kPhaseNames[6] = {"Presmoother", "Residual eval", "Restriction", "Coarse solve", "Prolongation", "Postsmoother"};
 struct PhaseTimer {
   H* h;
   int slot;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   PhaseTimer(H* h_, int lvl, int phase) : h(h_), slot(lvl * 6 + phase) {
+    char name[48];
+    snprintf(name, sizeof name, "%s L%d", kPhaseNames[phase], lvl);
+    nvtxRangePushA(name);
     if (h->profiling) {
       cudaEventCreate(&e0); cudaEventCreate(&e1);
       cudaEventRecord(e0, h->stream);
@@ -1364,6 +1401,7 @@ struct PhaseTimer {
       if (h->prof_ms && slot < (int)h->prof_ms->size()) (*h->prof_ms)[slot] += ms;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
+    nvtxRangePop();
   }
 };
 
@@ -1440,7 +1478,7 @@ static void ensure_cycle_graph(H* h, int cycle) {
 static void run_cycle(H* h, int cycle) {
   if (h->part) { cycle_body_part(h, cycle); return; }
   ensure_cycle_graph(h, cycle);
-  if (h->cycle_graph[cycle]) {
+  if (h->use_graphs && h->cycle_graph[cycle]) {
     CUDA_OK(cudaGraphLaunch(h->cycle_graph[cycle], h->stream));
     h->launches += h->cycle_graph_launches[cycle];
   } else {
@@ -1567,7 +1605,7 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
         solve_level(h, L0.coarse_x, B200AMG_CYCLE_V, L0.coarse_b, lvl + 1, false);
       }
     };
-    if (h->part_graphs && !h->cycle_graph[cycle] && h->cycle_graph_launches[cycle] >= 0 && !h->profiling) {
+    if (h->part_graphs && !h->part_whole_graph && !h->capturing && !h->cycle_graph[cycle] && h->cycle_graph_launches[cycle] >= 0 && !h->profiling) {
       cudaGraph_t gr = nullptr;
       h->capturing = true;
       h->capture_count = 0;
@@ -1586,7 +1624,7 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
       CUDA_OK(cudaGraphDestroy(gr));
       h->cycle_graph_launches[cycle] = h->capture_count;
     }
-    if (h->part_graphs && h->cycle_graph[cycle]) {
+    if (h->part_graphs && !h->part_whole_graph && !h->capturing && h->cycle_graph[cycle]) {
       CUDA_OK(cudaGraphLaunch(h->cycle_graph[cycle], h->stream));
       h->launches += h->cycle_graph_launches[cycle];
     } else {
@@ -1607,7 +1645,38 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
   spmv_add(h, P.P, P.cx, P.x);                                                   // :233-234
   smooth_part(h, P, P.post);                                                     // :236
 }
-static void cycle_body_part(H* h, int cycle) { cycle_part_level(h, 0, cycle); }
+// The whole partitioned cycle — kernels, memsets and the NCCL point-to-point groups of every level — is a static sequence on
+// every rank, so it is captured ONCE per cycle type into a CUDA graph and replayed (NCCL >= 2.9 records its kernels into a
+// capturing stream): ~60 launches + ~18 communication groups per V-cycle become one graph launch per rank.
+// B200AMG_PART_WHOLE_GRAPH=0 (or USE_GRAPHS=0 after finalize) goes back to eager launches.
+static void cycle_body_part(H* h, int cycle) {
+  if (!h->part_whole_graph || h->profiling) { cycle_part_level(h, 0, cycle); return; }
+  if (!h->part_cycle_graph[cycle]) {
+    cudaGraph_t g = nullptr;
+    const int64_t coll0 = h->collectives;
+    h->capturing = true;
+    h->capture_count = 0;
+    CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+      cycle_part_level(h, 0, cycle);
+    } catch (...) {
+      cudaStreamEndCapture(h->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      h->capturing = false;
+      throw;
+    }
+    CUDA_OK(cudaStreamEndCapture(h->stream, &g));
+    h->capturing = false;
+    CUDA_OK(cudaGraphInstantiate(&h->part_cycle_graph[cycle], g, 0));
+    CUDA_OK(cudaGraphDestroy(g));
+    h->part_cycle_launches[cycle] = h->capture_count;
+    h->part_cycle_collectives[cycle] = h->collectives - coll0;
+    h->collectives = coll0;
+  }
+  CUDA_OK(cudaGraphLaunch(h->part_cycle_graph[cycle], h->stream));
+  h->launches += h->part_cycle_launches[cycle];
+  h->collectives += h->part_cycle_collectives[cycle];
+}
 
 // sum over ranks of a device scalar, in place; every rank gets the same bits
 static void allreduce_scalar(H* h, double* dev) {
@@ -1664,6 +1733,17 @@ static void part_store(H* h, double* dst_full, const double* src_local, int memk
 // API helpers
 // ------------------------------------------------------------------------------------------
 static void set_device(H* h) { CUDA_OK(cudaSetDevice(h->device)); }
+// stream-synchronise and report a sweep kernel whose watchdog fired (a hand-off that never came: the result is not valid)
+static void sync_and_check(H* h) {
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (!h->gs_fault) return;
+  int f = 0;
+  CUDA_OK(cudaMemcpy(&f, h->gs_fault, sizeof(int), cudaMemcpyDeviceToHost));
+  if (f) {
+    CUDA_OK(cudaMemset(h->gs_fault, 0, sizeof(int)));
+    throw AmgError{B200AMG_ERR_CUDA, "a Gauss-Seidel sweep kernel timed out waiting for another tile (watchdog): result discarded"};
+  }
+}
 static void check_ready(H* h) {
   REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
   REQUIRE(h->finalized, B200AMG_ERR_STATE, "hierarchy not finalized (call b200amg_finalize first)");
@@ -1809,6 +1889,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
+  h->gs_fault = dev_alloc<int>(4);
+  CUDA_OK(cudaMemset(h->gs_fault, 0, 4 * sizeof(int)));
   CUDA_OK(cudaMallocHost(&h->h_scalars, sizeof(double) * 16));
   *out = h.release();
   API_END
@@ -1995,6 +2077,7 @@ int32_t b200amg_set_partition(b200amg_handle_t h, int32_t rank, int32_t world_si
   h->rank = rank;
   h->world = world_size;
   h->part_levels = std::max(1, env_int("B200AMG_PART_LEVELS", h->part_levels));
+  h->part_whole_graph = env_int("B200AMG_PART_WHOLE_GRAPH", 1) != 0;
   API_END
 }
 
@@ -2165,12 +2248,14 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
   if (h->comm) nccl_api().CommDestroy(h->comm);
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
-  cudaFree(h->partial); cudaFree(h->scalars); cudaFreeHost(h->h_scalars);
+  cudaFree(h->partial); cudaFree(h->scalars); cudaFree(h->gs_fault); cudaFreeHost(h->h_scalars);
   cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush); cudaFree(h->io_tmp);
   for (cudaEvent_t e : h->res_events) cudaEventDestroy(e);
   for (int c = 0; c < 3; ++c)
     if (h->cycle_graph[c]) cudaGraphExecDestroy(h->cycle_graph[c]);
   if (h->resnorm_graph) cudaGraphExecDestroy(h->resnorm_graph);
+  for (int c = 0; c < 3; ++c)
+    if (h->part_cycle_graph[c]) cudaGraphExecDestroy(h->part_cycle_graph[c]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return B200AMG_OK;
@@ -2230,7 +2315,7 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
   }
   if (h->part) part_store(h, x, h->part->x, memkind);
   else vec_out(h, level_numbering(h, 0), x, h->x0, n, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   if (nres) *nres = nr;
   if (iters) *iters = itr - 1;
   API_END
@@ -2252,7 +2337,7 @@ int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cy
     run_cycle(h, cycle);
     vec_out(h, level_numbering(h, 0), x, h->x0, h->n0, memkind);
   }
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   API_END
 }
 
@@ -2269,7 +2354,7 @@ int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t 
     else CUDA_OK(cudaMemcpyAsync(P.x, P.b, sizeof(double) * (size_t)P.plan.nloc, cudaMemcpyDeviceToDevice, h->stream));
     run_cycle(h, cycle);
     part_store(h, x, P.x, memkind);
-    CUDA_OK(cudaStreamSynchronize(h->stream));
+    sync_and_check(h);
     return B200AMG_OK;
   }
   vec_in(h, level_numbering(h, 0), h->b0, b, h->n0, memkind);
@@ -2277,7 +2362,7 @@ int32_t b200amg_precond(b200amg_handle_t h, double* x, const double* b, int32_t 
   else CUDA_OK(cudaMemcpyAsync(h->x0, h->b0, sizeof(double) * h->n0, cudaMemcpyDeviceToDevice, h->stream));
   run_cycle(h, cycle);
   vec_out(h, level_numbering(h, 0), x, h->x0, h->n0, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   API_END
 }
 
@@ -2293,7 +2378,7 @@ int32_t b200amg_smooth(b200amg_handle_t h, int32_t level, int32_t which, double*
   vec_in(h, &L.M, sb.p, b, L.n, memkind);
   smooth(h, L.M, which == B200AMG_PRE ? L.pre : L.post, sx.p, sb.p, L.temp, false);
   vec_out(h, &L.M, x, sx.p, L.n, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   API_END
 }
 
@@ -2414,7 +2499,7 @@ int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycl
     ++it;
   }
   vec_out(h, level_numbering(h, 0), x, h->pcg_x, n, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   if (nres) *nres = nr;
   if (iters) *iters = it;
   API_END
@@ -2465,7 +2550,7 @@ int32_t b200amg_smoother_apply(b200amg_smoother_handle_t s, double* x, const dou
   vec_in(h, &s->M, s->b, b, s->M.n, memkind);
   smooth(h, s->M, s->cfg, s->x, s->b, s->temp, false);
   vec_out(h, &s->M, x, s->x, s->M.n, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   API_END
 }
 
@@ -2591,11 +2676,30 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
   API_END
 }
 
+// graphs captured with the old option values would keep launching the old kernels: drop them, they are re-captured on demand
+static void drop_cycle_graphs(H* h) {
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int c = 0; c < 3; ++c) {
+    if (h->cycle_graph[c]) cudaGraphExecDestroy(h->cycle_graph[c]);
+    h->cycle_graph[c] = nullptr;
+    h->cycle_graph_launches[c] = 0;
+  }
+  if (h->resnorm_graph) { cudaGraphExecDestroy(h->resnorm_graph); h->resnorm_graph = nullptr; }
+  for (int c = 0; c < 3; ++c) {
+    if (h->part_cycle_graph[c]) cudaGraphExecDestroy(h->part_cycle_graph[c]);
+    h->part_cycle_graph[c] = nullptr;
+  }
+}
+
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
   API_BEGIN
   REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
+  if (option != B200AMG_OPT_TIME_RESIDUAL && option != B200AMG_OPT_USE_GRAPHS && option != B200AMG_OPT_PART_LEVELS) drop_cycle_graphs(h);
   switch (option) {
-    case B200AMG_OPT_USE_GRAPHS: h->use_graphs = value != 0.0; break;
+    case B200AMG_OPT_USE_GRAPHS:
+      h->use_graphs = value != 0.0;
+      if (h->part) h->part_whole_graph = value != 0.0;   // (finalize switches use_graphs off for partitioned handles)
+      break;
     case B200AMG_OPT_TIME_RESIDUAL: h->time_residual = value != 0.0; break;
     case B200AMG_OPT_STREAM_CHUNK: h->stream_chunk = (int)value; break;
     case B200AMG_OPT_GS_MODE: h->gs_mode = (int)value; break;

@@ -447,12 +447,17 @@ int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, 
 #endif
   R.rows.resize(nthreads);
   R.vals.resize(nthreads);
+  // The runtime may deliver a SMALLER team than requested (OMP_DYNAMIC, OMP_THREAD_LIMIT, nested regions, cgroup limits):
+  // every thread that does run takes the chunks t, t + team, t + 2 team, ... so that all `nthreads` chunks are computed
+  // whatever the team size is (a chunk left out would silently leave empty columns in the Galerkin product).
 #pragma omp parallel num_threads(nthreads)
   {
-    int t = 0;
+    int t0 = 0, team = 1;
 #ifdef _OPENMP
-    t = omp_get_thread_num();
+    t0 = omp_get_thread_num();
+    team = omp_get_num_threads();
 #endif
+    for (int t = t0; t < nthreads; t += team) {
     // contiguous static chunk of columns per thread so chunks concatenate in order
     const int64_t c0 = n * t / nthreads, c1 = n * (t + 1) / nthreads;
     // dense accumulator + marker per thread, kept between calls (a setup multiplies 2 x levels times): the marker
@@ -482,6 +487,7 @@ int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, 
       for (idx_t r : list) { out_r.push_back(r); out_v.push_back(acc[r]); }
       R.colcount[j] = (idx_t)list.size();
     }
+    }   // chunks of this thread
   }
   int64_t nnz = 0;
   for (auto& v : R.rows) nnz += (int64_t)v.size();

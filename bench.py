@@ -131,6 +131,11 @@ def workload_name(args):
     return f"poisson(({dims})) fp64, {meth} V-cycle, pre/post {sm}, b=A*ones, x0=0"
 
 
+def bench_config(args, A, nlevels):
+    """The SAME dict in both arms (`--impl ours` / `--impl reference`): what the workload is, nothing about how it is run."""
+    return {"workload": workload_name(args), "n": A.n, "nnz": A.nnz, "levels": nlevels}
+
+
 def bytes_spmv(n, nnz):       # SURVEY §8d: fp64 values, int32 column indices + row pointers, x counted once
     return 12 * nnz + 4 * (n + 1) + 16 * n
 
@@ -150,29 +155,37 @@ def run_reference(args):
         args.smoother = "jacobi"          # same workload as our arm at N > 1 (config C4)
     amg, A, ml, b, t_setup = build_problem(args)
     H = oracle.OracleHierarchy(ml)
-    budget = float(os.environ.get("B200AMG_REF_BUDGET_S", "150"))
+    budget = float(os.environ.get("B200AMG_REF_BUDGET_S", "240"))
     x = np.zeros(A.n)
+    # one untimed iteration tells what the requested warm-up + steps cost; both are then honoured as far as the budget allows
     t_start = time.time()
-    for _ in range(min(args.warmup, 1)):
-        x = H.solve(b, x0=x, maxiter=1, reltol=0.0)
-    per = time.time() - t_start if args.warmup else None
-    steps = args.steps
-    if per:
-        steps = max(1, min(args.steps, int((budget - per) / per)))
+    x, h0 = H.solve(b, x0=x, maxiter=1, reltol=0.0, log=True)
+    per = max(time.time() - t_start, 1e-9)
+    hist = list(h0)
+    warm = max(0, min(args.warmup - 1, int(0.25 * budget / per)))
+    if warm:
+        x, hw = H.solve(b, x0=x, maxiter=warm, reltol=0.0, log=True)
+        hist += list(hw[1:])
+    warm += 1
+    steps = max(1, min(args.steps, int((budget - warm * per) / per)))
     t0 = time.time()
-    x = H.solve(b, x0=x, maxiter=steps, reltol=0.0)
+    x, ht = H.solve(b, x0=x, maxiter=steps, reltol=0.0, log=True)
     dt = time.time() - t0
+    hist += list(ht[1:])
     val = steps / dt
     line = {
         "impl": "reference", "metric": "V-cycle iterations/s", "value": val, "unit": "V-cycles/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n": A.n, "nnz": A.nnz, "levels": len(ml)},
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": bench_config(args, A, len(ml)),
         "cpu_baseline": {"value": val, "unit": "V-cycles/s", "cores": 1, "kind": "port",
-                         "sample": f"{steps} `_solve!` iterations (V-cycle + residual + norm) of the full workload, "
-                                   "single thread (the reference solve phase is single-threaded), gcc -O2 -ffp-contract=off"},
+                         "sample": f"{steps} `_solve!` iterations (V-cycle + residual + norm) of the full workload after {warm} warm-up "
+                                   "iterations, single thread (the reference solve phase is single-threaded), gcc -O2 -ffp-contract=off"},
         "e2e": {"value": val, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cores_available": os.cpu_count(), "setup_s": t_setup,
+        # what the GPU arm can be compared with: the same iteration counts from x0 = 0 (bench.py's `parity` block does that)
+        "residual_history_first_last": [float(hist[0]), float(hist[-1])], "iterations_from_x0": len(hist) - 1,
+        "max_abs_err_vs_ones": float(np.abs(x - 1.0).max()),
     }
     print(json.dumps(line), flush=True)
 
@@ -316,7 +329,9 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
                 "avg_launch_ms": res_ms_avg, "launches_timed": int(len(res_ms)), "share_of_step": res_ms_avg / (ms / K),
-                "traffic": ncu_traffic(args, world)}
+                "traffic": ncu_traffic(args, world),
+                "traffic_source": "static: one `ncu --set full` capture of this kernel on this workload, committed as "
+                                  "profiles/r01_ncu_traffic.json (not measured in this run)"}
     phases = ["presmoother", "residual", "restriction", "coarse_solve", "prolongation", "postsmoother"]
     prof = dev.profile_cycle(0) if world == 1 else np.zeros((dev.nlevels, 6))
     infos = [dev.level_info(i) for i in range(dev.nlevels)]
@@ -334,20 +349,32 @@ def run_ours(args):
     }
     # ---- CPU baseline beside it: the oracle port on one host core, bounded sample -------------------------
     cpu = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         import oracle
 
         H = oracle.OracleHierarchy(ml)
         t0 = time.time()
-        xo = H.solve(b, maxiter=1, reltol=0.0)
+        xo, ho = H.solve(b, maxiter=1, reltol=0.0, log=True)
         per = time.time() - t0
         s = max(1, min(5, int(20.0 / max(per, 1e-9))))
         t0 = time.time()
-        xo = H.solve(b, x0=xo, maxiter=s, reltol=0.0)
+        xo, h2 = H.solve(b, x0=xo, maxiter=s, reltol=0.0, log=True)
         dt = time.time() - t0
+        ho = np.concatenate([ho, h2[1:]])
         cpu = {"value": s / dt, "unit": "V-cycles/s", "cores": 1, "kind": "port",
                "sample": f"{s} `_solve!` iterations of the same hierarchy after 1 warm-up iteration, single thread "
                          f"(reference solve phase is single-threaded); host has {os.cpu_count()} logical cores"}
+        # ---- parity at FULL size: the same 1 + s iterations from x0 = 0 on the device, against the oracle's ----
+        xg = torch.zeros(n, dtype=torch.float64, device="cuda")
+        hg, itg = dev.solve(xg, b_d, 0, 1 + s, 0.0, 0.0, True)
+        xg = xg.cpu().numpy()
+        parity = {"iters": int(itg), "oracle_iters": int(len(ho) - 1),
+                  "rel_hist_diff": float(np.max(np.abs(hg - ho) / np.abs(ho))) if len(hg) == len(ho) else None,
+                  "rel_x_diff": float(np.abs(xg - xo).max() / np.abs(xo).max()),
+                  "tolerance": {"rel_hist_diff": 1e-6, "rel_x_diff": 1e-9},
+                  "what": f"`_solve!` from x0 = 0, {1 + s} iterations, device vs CPU oracle on the full {workload_name(args)}"}
+        parity["ok"] = bool(parity["rel_hist_diff"] is not None and parity["rel_hist_diff"] <= 1e-6 and parity["rel_x_diff"] <= 1e-9)
         # courtesy figure, NOT reference behaviour (its solve phase is single-threaded): the headline kernel r = b - A x on all
         # host cores (OpenMP over rows, host setup library), i.e. what the host's memory system can do on the same bytes
         try:
@@ -358,23 +385,33 @@ def run_ours(args):
                                               "note": "OpenMP row-parallel residual on all host cores; not reference behaviour"}
         except Exception as exc:  # never let a courtesy figure break the bench line
             cpu["fine_residual_all_cores"] = {"error": str(exc)[:200]}
-        # parity of the timed run against the oracle after the same number of iterations is checked in tests/
+    hier_gb = 12e-9 * sum(i["nnz_a"] for i in infos)
+    l2_note = (f"fine-level A is {12e-9 * nnz:.2f} GB, the hierarchy {hier_gb:.2f} GB, L2 is 0.126 GB: "
+               + ("every kernel of a cycle streams a different operator several times the size of L2, nothing survives from one "
+                  "iteration to the next; no flush" if 12e-9 * nnz > 4 * 0.126 else
+                  "this workload is SMALL against L2 (it stays resident): per-kernel rates in this line are L2 rates, not HBM rates"))
+    roofline["parity"] = parity if cpu is not None else None
     line = {
         "metric": "V-cycle iterations/s", "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args), "n": n, "nnz": nnz, "levels": dev.nlevels,
-                   "l2": (f"inputs larger than L2: fine-level A is {12e-9 * nnz:.2f} GB, the hierarchy {12e-9 * sum(i['nnz_a'] for i in infos):.2f} GB, "
-                          "126 MB of L2; every kernel of a cycle streams a different operator, no flush needed"),
-                   "parallelism": (f"{args.part_levels} finest level(s) row-partitioned x{world}, the rest on rank 0" if world > 1
-                                   else "single GPU")},
+        "config": bench_config(args, A, dev.nlevels),
+        "l2": l2_note,
+        "parallelism": (f"{args.part_levels} finest level(s) row-partitioned x{world}, the rest on rank 0" if world > 1 else "single GPU"),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        "parity": parity if cpu is not None else None,
     }
     if world > 1:
         line["n1_same_workload"] = n1_same
-        line["config"]["note"] = ("BASELINE config C4: Jacobi smoother (Gauss-Seidel, the N=1 headline config C3, is sequential over the "
-                                  "index range and does not shard); the finest --part-levels levels are split by rows, the levels below them run "
-                                  "on rank 0, which bounds the whole-cycle speed-up (Amdahl); strong-scaling baseline = n1_same_workload")
+        eff = (value / n1_same["value"] / world) if n1_same else None
+        line["strong_efficiency_vs_n1_same_workload"] = eff
+        # kept inside `roofline` as well: the driver's record keeps that object whole
+        roofline["n1_same_workload_value"] = n1_same["value"] if n1_same else None
+        roofline["strong_efficiency"] = eff
+        roofline["parity_max_abs_diff_vs_partitioned"] = n1_same["parity_max_abs_diff_vs_partitioned"] if n1_same else None
+        line["note"] = ("BASELINE config C4: Jacobi smoother (Gauss-Seidel, the N=1 headline config C3, is sequential over the "
+                        "index range and does not shard); the finest --part-levels levels are split by rows, the levels below them run "
+                        "on rank 0, which bounds the whole-cycle speed-up (Amdahl); strong-scaling baseline = n1_same_workload")
         line["nccl_collectives_in_timed_region"] = None
     line.update(extra)
     print(json.dumps(line), flush=True)

@@ -138,6 +138,22 @@ def test_smoothers_vs_oracle(amg, fx, case, symmetry):
         assert relinf(x, ref) <= tol, (case, symmetry, sm)
 
 
+def test_smoother_block_right_hand_sides_column_by_column(amg):
+    """smooth!(x, s, b) with n x m blocks relaxes every column (src/smoother.jl:77,118,195 `for col in 1:size(x, 2)`):
+    the standalone device smoother must do the same, column against column of the oracle."""
+    A = amg.poisson((12, 11, 10))
+    r = _rng(9)
+    X0, B = r.standard_normal((A.n, 2)), r.standard_normal((A.n, 2))
+    for sm in [amg.GaussSeidel(), amg.Jacobi(2 / 3, iter=2), amg.SOR(1.1, amg.ForwardSweep())]:
+        X = X0.copy()
+        sm(A, X, B, amg.HermitianSymmetry())
+        for j in range(2):
+            ref = oracle.smooth(A, sm, X0[:, j].copy(), B[:, j].copy())
+            assert relinf(X[:, j], ref) <= TOL_SWEEP, (sm, j)
+    with pytest.raises((AssertionError, ValueError)):
+        amg.GaussSeidel()(A, X0.copy(), B[:, 0].copy(), amg.HermitianSymmetry())
+
+
 def test_fast_equals_general_on_symmetric_device(amg):
     # test/test_smoothers.jl:29-45
     A = amg.poisson(50)
@@ -226,6 +242,38 @@ def test_solve_vs_oracle(amg, jac):
             if len(hist) <= 100:                       # converged within maxiter (test/cycle_tests.jl:16)
                 assert np.linalg.norm(b - A.matvec(x)) < 1e-8 * np.linalg.norm(b)
         ml.release()
+
+
+@pytest.mark.parametrize("method", ["rs", "sa"])
+def test_julia_index_convention_crosses_the_abi(amg, jac, method):
+    """The arrays a Julia caller holds are Int64 and 1-based, with the lazy Adjoint flag on P (Ruge-Stuben,
+    src/classical.jl:64-65) or on R (smoothed aggregation, src/aggregation.jl:158-159).  Uploading the same hierarchy in that
+    form must give bit-for-bit the results of this package's own int32 / 0-based upload."""
+    from algebraicmultigrid_jl_b200 import _devlib
+
+    A = amg.poisson((14, 13, 12))
+    ml = amg.ruge_stuben(A) if method == "rs" else amg.smoothed_aggregation(A, presmoother=jac, postsmoother=jac)
+    adj = [hasattr(lv.P, "parent") for lv in ml.levels], [hasattr(lv.R, "parent") for lv in ml.levels]
+    assert all(adj[0]) if method == "rs" else all(adj[1])          # the lazy-Adjoint descriptors are really exercised
+    b = _rng(4).standard_normal(A.n)
+    d0 = _devlib.DeviceHierarchy(ml)
+    d1 = _devlib.DeviceHierarchy(ml, julia_indices=True)
+    try:
+        x0, x1 = np.zeros(A.n), np.zeros(A.n)
+        h0, it0 = d0.solve(x0, b, 0, 30, 0.0, 1e-10, True)
+        h1, it1 = d1.solve(x1, b, 0, 30, 0.0, 1e-10, True)
+        assert it0 == it1 and np.array_equal(h0, h1) and np.array_equal(x0, x1)
+        for cyc in (1, 2):
+            y0, y1 = np.zeros(A.n), np.zeros(A.n)
+            d0.cycle(y0, b, cyc)
+            d1.cycle(y1, b, cyc)
+            assert np.array_equal(y0, y1)
+        H = oracle.OracleHierarchy(ml)
+        xr, hr = H.solve(b, maxiter=30, reltol=1e-10, log=True)
+        assert len(hr) == len(h1) and relinf(x1, xr) <= TOL_SOLVE_X
+    finally:
+        d0.close()
+        d1.close()
 
 
 def test_thing_goldens_on_device(amg, fx):
@@ -378,9 +426,11 @@ def test_properties_at_size(amg, jac):
 
 # ---- every Gauss-Seidel sweep protocol gives the reference's sequential sweep ---------------------
 @pytest.mark.parametrize("mode,env", [(0, {}), (1, {}), (2, {}), (3, {}), (2, {"cta_rows": 0, "mail_width": 1})])
-def test_all_sweep_protocols_agree_with_oracle(amg, mode, env):
+def test_all_sweep_protocols_agree_with_oracle(amg, monkeypatch, mode, env):
     """gs_mode 0 one launch per wavefront, 1 wavefront-counter dataflow, 2 TMA-fed mailbox (+ single-CTA on small
-    levels), 3 ticket mailbox; the last case forces the mailbox sweeps onto every level."""
+    levels), 3 ticket mailbox; the last case forces the mailbox sweeps onto every level.  (The blocked sweep, which would
+    otherwise take the stencil level and the tiny ones, is switched off: it has its own test below.)"""
+    monkeypatch.setenv("B200AMG_GS_BLOCK", "0")
     A = amg.poisson((28, 28, 28))
     ml = amg.ruge_stuben(A)
     dev = ml.device()
@@ -444,6 +494,47 @@ def test_full_size_256_properties(amg):
     assert np.abs(xs - 1).max() < 1e-3
     rr = dev.residual(0, np.empty(n), b, xs)
     assert abs(np.linalg.norm(rr) - hist[-1]) <= 1e-9 * hist[0]
+    # ---- BASELINE config C3 at FULL size against the oracle: 3 `_solve!` iterations from x0 = 0 (the size-selected sweep
+    # kernels only all run together here; a stale read in a sweep still converges, so properties alone would not catch it)
+    H = oracle.OracleHierarchy(ml)
+    xo, ho = H.solve(b, maxiter=3, reltol=0.0, log=True)
+    xg, hg = amg._solve(ml, b, log=True, maxiter=3, reltol=0.0)
+    assert len(hg) == len(ho) == 4
+    assert np.max(np.abs(hg - ho) / ho) <= TOL_HIST and relinf(xg, xo) <= TOL_SOLVE_X
+    # one symmetric Gauss-Seidel sweep on each of the three largest levels, repeated: every repetition must land on the
+    # oracle's sweep (the hand-offs between CTAs are exercised ~50 000 times per repetition)
+    for lvl in range(3):
+        Al = ml.levels[lvl].A
+        xl, bl = _rng(lvl).standard_normal(Al.n), _rng(10 + lvl).standard_normal(Al.n)
+        ref = oracle.smooth(Al, amg.GaussSeidel(), xl.copy(), bl)
+        for rep in range(8 if lvl == 0 else 4):
+            got = dev.smooth(lvl, 0, xl.copy(), bl)
+            assert relinf(got, ref) <= TOL_SWEEP, (lvl, rep)
+    del H
+    ml.release()
+    # ---- BASELINE config C4's workload (same matrix, Jacobi) on one GPU: 3 iterations against the oracle
+    jac = amg.Jacobi(2.0 / 3.0)
+    ml = amg.ruge_stuben(A, presmoother=jac, postsmoother=jac)
+    H = oracle.OracleHierarchy(ml)
+    xo, ho = H.solve(b, maxiter=3, reltol=0.0, log=True)
+    xg, hg = amg._solve(ml, b, log=True, maxiter=3, reltol=0.0)
+    assert np.max(np.abs(hg - ho) / ho) <= TOL_HIST and relinf(xg, xo) <= TOL_SOLVE_X
+    del H
+    ml.release()
+
+
+def test_full_size_c2_sa_jacobi_1024x1024_vs_oracle(amg):
+    """BASELINE config C2 at full size: 2-D poisson((1024, 1024)), smoothed aggregation + Jacobi, against the oracle."""
+    A = amg.poisson((1024, 1024))
+    assert A.n == 1048576 and A.nnz == 5238784
+    jac = amg.Jacobi(2.0 / 3.0)
+    ml = amg.smoothed_aggregation(A, presmoother=jac, postsmoother=jac)
+    b = A.matvec(np.ones(A.n))
+    H = oracle.OracleHierarchy(ml)
+    xo, ho = H.solve(b, maxiter=10, reltol=0.0, log=True)
+    xg, hg = amg._solve(ml, b, log=True, maxiter=10, reltol=0.0)
+    assert len(hg) == len(ho) == 11
+    assert np.max(np.abs(hg - ho) / ho) <= TOL_HIST and relinf(xg, xo) <= TOL_SOLVE_X
     ml.release()
 
 
@@ -484,13 +575,49 @@ def test_synthetic_elasticity_with_near_null_space(amg):
     ml.release()
 
 
+@pytest.mark.parametrize("block", ["1", "2"])
+def test_blocked_sweep_matches_oracle(amg, fx, monkeypatch, block):
+    """The blocked exact-order sweep (block_gs.cuh: one CTA per tile of rows, shared-memory window, scouts that stage far
+    values, cross-tile progress counters) against the reference's sequential sweeps: Gauss-Seidel and SOR, forward /
+    backward / symmetric, on stencils of every dimension, irregular RS coarse operators, a finite-element matrix and
+    multi-tile levels; B200AMG_GS_BLOCK=2 forces it onto every level of a hierarchy, =1 is the default per-level choice."""
+    monkeypatch.setenv("B200AMG_GS_BLOCK", block)
+    ml0 = amg.ruge_stuben(amg.poisson((40, 40, 40)))
+    mats = [amg.poisson(777), amg.poisson((40, 33)), amg.poisson((20, 17, 12)), amg.poisson((40, 40, 40)), fx.matrix("thing")]
+    mats += [lv.A for lv in ml0.levels[1:4]]
+    F_, B_, S_ = amg.ForwardSweep(), amg.BackwardSweep(), amg.SymmetricSweep()
+    zoo = [amg.GaussSeidel(F_), amg.GaussSeidel(B_), amg.GaussSeidel(S_, 2), amg.SOR(0.5, F_), amg.SOR(1.3, S_, 2)]
+    r = _rng(77)
+    for A in mats:
+        x0, b = r.standard_normal(A.n), r.standard_normal(A.n)
+        for sm in zoo:
+            x = x0.copy()
+            sm(A, x, b, amg.HermitianSymmetry())
+            ref = oracle.smooth(A, sm, x0.copy(), b)
+            assert relinf(x, ref) <= TOL_SWEEP, (A.n, sm, block)
+    # whole solves through it (every level relaxed by the blocked sweep when block == "2")
+    for dims in [(28, 28, 28), (60, 50)]:
+        A = amg.poisson(dims)
+        ml = amg.ruge_stuben(A)
+        b = r.random(A.n)
+        x, hist = amg._solve(ml, b, log=True)
+        xr, histr = oracle.OracleHierarchy(ml).solve(b, log=True)
+        assert len(hist) == len(histr) and np.max(np.abs(hist - histr) / histr) <= TOL_HIST
+        assert np.linalg.norm(x - xr) / np.linalg.norm(xr) <= TOL_SOLVE_X
+        for cyc in (amg.W(), amg.F()):
+            y = amg._solve(ml, b, cyc, maxiter=2, calculate_residual=False)
+            yr = oracle.OracleHierarchy(ml).solve(b, cycle=type(cyc).__name__, maxiter=2, calculate_residual=False)
+            assert relinf(y, yr) <= TOL_CYCLE
+        ml.release()
+
+
 def test_cluster_sweep_on_mid_size_level(amg):
     """The optional one-cluster sweep (x in distributed shared memory, cluster_gs.cuh; off by default because it measured
     no faster than the counter sweep) must give the reference's sequential sweep for every cluster shape."""
     ml = amg.ruge_stuben(amg.poisson((48, 48, 48)))
     lv = 1
     level = ml.levels[lv]
-    assert 12288 < level.A.n <= 380000 and level.A.nnz / level.A.n >= 16
+    assert 12288 < level.A.n <= 380000 and level.A.nnz / level.A.n >= 16     # (never a blocked-sweep level: long rows)
     dev = ml.device()
     dev.set_option(0, 0)
     r = _rng(48)
@@ -511,6 +638,7 @@ def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence):
     """Every cluster size (1..16 CTAs; -1 = chosen per level) of the distributed-shared-memory sweep gives the
     reference's sequential Gauss-Seidel / SOR sweeps (forward, backward, symmetric; Hermitian and NoSymmetry walks),
     on stencil rows, irregular RS coarse operators and a nonsymmetric matrix; then whole cycles through it."""
+    monkeypatch.setenv("B200AMG_GS_BLOCK", "0")
     monkeypatch.setenv("B200AMG_GS_DSM", "2")
     monkeypatch.setenv("B200AMG_GS_DSM_MAX_CTAS_LOG2", "4")
     monkeypatch.setenv("B200AMG_GS_DSM_FENCE", str(fence))
