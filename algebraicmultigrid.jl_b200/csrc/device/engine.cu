@@ -244,11 +244,17 @@ struct DevCsr {
   // tile plan of the TMA stream kernels (stream.cuh); ntiles == 0: not streamable (a row > kTileNnz)
   int4* meta = nullptr;
   int ntiles = 0;
+  // row-partitioned levels: the same tiles sorted into INTERIOR ones (no column in the halo part of the vector) and BOUNDARY
+  // ones; the interior kernel runs while the halo exchange is in flight (meta_split = [interior..., boundary...])
+  int4* meta_split = nullptr;
+  int ntiles_int = 0, ntiles_bnd = 0;
   int stream_lanes = 1;
   int stream_burst = 8;
+  int64_t halo_begin = -1;
   bool owner = false;
-  void upload(const HostCsr& h) {
+  void upload(const HostCsr& h, int64_t halo_start = -1) {
     nrows = h.nrows; ncols = h.ncols; nnz = h.nnz();
+    halo_begin = halo_start;
     ptr = dev_upload(h.ptr, 8);
     idx = dev_upload(h.idx, 8);
     val = dev_upload(h.val, 8);
@@ -285,11 +291,23 @@ struct DevCsr {
     }
     meta = dev_upload(m);
     ntiles = (int)m.size();
+    if (halo_begin >= 0) {
+      std::vector<int4> mi, mb;
+      for (const int4& t : m) {
+        bool bnd = false;
+        for (int k = t.z; k < t.w && !bnd; ++k) bnd = h.idx[k] >= halo_begin;
+        (bnd ? mb : mi).push_back(t);
+      }
+      ntiles_int = (int)mi.size();
+      ntiles_bnd = (int)mb.size();
+      mi.insert(mi.end(), mb.begin(), mb.end());
+      meta_split = dev_upload(mi);
+    }
   }
   void alias(const DevCsr& o) { *this = o; owner = false; }
   void release() {
-    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(meta); }
-    ptr = idx = nullptr; val = nullptr; meta = nullptr; ntiles = 0; owner = false;
+    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(meta); cudaFree(meta_split); }
+    ptr = idx = nullptr; val = nullptr; meta = nullptr; meta_split = nullptr; ntiles = ntiles_int = ntiles_bnd = 0; owner = false;
   }
 };
 
@@ -799,6 +817,9 @@ struct b200amg_hierarchy {
   cudaGraphExec_t resnorm_graph = nullptr;
   bool use_graphs = true;
   bool part_graphs = true;   // partitioned handles: rank 0 replays the levels below the fine one as a graph
+  bool part_overlap = true;   // halo exchange on a second stream, overlapped with the interior rows of the kernel that needs it
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
   bool part_whole_graph = true;   // partitioned handles: the whole cycle (kernels + NCCL groups) is one captured graph per rank
   cudaGraphExec_t part_cycle_graph[3] = {nullptr, nullptr, nullptr};
   int64_t part_cycle_launches[3] = {0, 0, 0}, part_cycle_collectives[3] = {0, 0, 0};
@@ -873,10 +894,16 @@ static void stream_set_attr_all() {
 static void stream_kernels_init() {   // once per device context: opt in to 86 KB of dynamic shared memory
   stream_set_attr_all<0>(); stream_set_attr_all<1>(); stream_set_attr_all<2>(); stream_set_attr_all<3>(); stream_set_attr_all<4>();
 }
+// part: 0 every tile, 1 the interior tiles, 2 the boundary tiles (row-partitioned levels, DevCsr::meta_split)
 template <int MODE>
-static void launch_stream(H* h, const DevCsr& A, const double* x, const double* b, double* y, double omega,
-                          const double* diagvals) {
-  const int ctas = std::min(A.ntiles, kNumSM * 2);
+static void launch_stream(H* h, const DevCsr& A0, const double* x, const double* b, double* y, double omega,
+                          const double* diagvals, int part = 0) {
+  DevCsr A = A0;   // (a shallow view: tile list and count swapped for the requested part)
+  A.owner = false;
+  if (part == 1) { A.meta = A0.meta_split; A.ntiles = A0.ntiles_int; }
+  else if (part == 2) { A.meta = A0.meta_split + A0.ntiles_int; A.ntiles = A0.ntiles_bnd; }
+  if (A.ntiles == 0) return;
+  const int ctas = std::min(A.ntiles, h->num_sms * 2);
   int chunk = h->stream_chunk > 0 ? h->stream_chunk : (A.ntiles + ctas - 1) / ctas;
 #define B200AMG_STREAM_CASE(TT)                                                                                         \
   case TT:                                                                                                              \
@@ -904,9 +931,10 @@ static void launch_stream(H* h, const DevCsr& A, const double* x, const double* 
 }
 
 template <int MODE>
-static void launch_csr(H* h, const DevCsr& A, const double* x, const double* b, double* y) {
+static void launch_csr(H* h, const DevCsr& A, const double* x, const double* b, double* y, int part = 0) {
   if (A.nrows == 0) return;
-  if (A.ntiles > 0) { launch_stream<MODE>(h, A, x, b, y, 0.0, nullptr); return; }
+  if (A.ntiles > 0) { launch_stream<MODE>(h, A, x, b, y, 0.0, nullptr, part); return; }
+  if (part == 1) return;   // not streamable: everything runs as the "boundary" part, after the exchange
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: csr_vec_kernel<2, MODE><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, x, b, y); break;
@@ -917,12 +945,13 @@ static void launch_csr(H* h, const DevCsr& A, const double* x, const double* b, 
   }
   count_launch(h);
 }
-static void spmv(H* h, const DevCsr& A, const double* x, double* y) { launch_csr<0>(h, A, x, nullptr, y); }
-static void residual(H* h, const DevCsr& A, const double* x, const double* b, double* r) { launch_csr<1>(h, A, x, b, r); }
-static void spmv_add(H* h, const DevCsr& A, const double* x, double* y) { launch_csr<2>(h, A, x, nullptr, y); }
+static void spmv(H* h, const DevCsr& A, const double* x, double* y, int part = 0) { launch_csr<0>(h, A, x, nullptr, y, part); }
+static void residual(H* h, const DevCsr& A, const double* x, const double* b, double* r, int part = 0) { launch_csr<1>(h, A, x, b, r, part); }
+static void spmv_add(H* h, const DevCsr& A, const double* x, double* y, int part = 0) { launch_csr<2>(h, A, x, nullptr, y, part); }
 
-static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const double* b, double* xout, double w) {
-  if (A.ntiles > 0) { launch_stream<3>(h, A, xin, b, xout, w, nullptr); return; }
+static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const double* b, double* xout, double w, int part = 0) {
+  if (A.ntiles > 0) { launch_stream<3>(h, A, xin, b, xout, w, nullptr, part); return; }
+  if (part == 1) return;
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: jacobi_fast_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, xin, b, xout, w); break;
@@ -934,8 +963,9 @@ static void launch_jacobi_fast(H* h, const DevCsr& A, const double* xin, const d
   count_launch(h);
 }
 static void launch_jacobi_general(H* h, const DevCsr& A, const double* diag, const double* xin, const double* b,
-                                  double* xout, double w) {
-  if (A.ntiles > 0) { launch_stream<4>(h, A, xin, b, xout, w, diag); return; }
+                                  double* xout, double w, int part = 0) {
+  if (A.ntiles > 0) { launch_stream<4>(h, A, xin, b, xout, w, diag, part); return; }
+  if (part == 1) return;
   const unsigned g = grid_for(A.nrows * A.lanes);
   switch (A.lanes) {
     case 2: jacobi_general_kernel<2><<<g, kThreads, 0, h->stream>>>(A.nrows, A.ptr, A.idx, A.val, diag, xin, b, xout, w); break;
@@ -1530,6 +1560,29 @@ static void halo_exchange(H* h, Part& P, double* v) {
   h->collectives++;
 }
 
+// The same exchange, split in two so that work which does not touch the halo can run in between: _begin forks onto the
+// communication stream (after everything enqueued so far on the compute stream: producers of v's owned part, earlier readers
+// of its halo part), _end joins it back.  Both are captured into the whole-cycle graph as a fork / join.
+static void halo_exchange_begin(H* h, Part& P, double* v) {
+  if (!h->part_overlap) { halo_exchange(h, P, v); return; }
+  cudaStream_t compute = h->stream;
+  CUDA_OK(cudaEventRecord(h->ev_ready, compute));
+  CUDA_OK(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
+  h->stream = h->comm_stream;
+  try {
+    halo_exchange(h, P, v);
+  } catch (...) {
+    h->stream = compute;
+    throw;
+  }
+  h->stream = compute;
+  CUDA_OK(cudaEventRecord(h->ev_done, h->comm_stream));
+}
+static void halo_exchange_end(H* h) {
+  if (!h->part_overlap) return;
+  CUDA_OK(cudaStreamWaitEvent(h->stream, h->ev_done, 0));
+}
+
 static void smooth_part(H* h, Part& P, const SmootherCfg& c) {
   if (c.kind == B200AMG_SMOOTHER_NONE || P.plan.nloc == 0) {
     if (c.kind != B200AMG_SMOOTHER_NONE) for (int it = 0; it < c.iter; ++it) halo_exchange(h, P, P.x);   // keep the collectives matched
@@ -1538,9 +1591,14 @@ static void smooth_part(H* h, Part& P, const SmootherCfg& c) {
   double* cur = P.x;
   double* other = P.temp;
   for (int it = 0; it < c.iter; ++it) {
-    halo_exchange(h, P, cur);
-    if (P.symmetry == B200AMG_SYMMETRY_NONE) launch_jacobi_general(h, P.A, P.diag, cur, P.b, other, c.omega);
-    else launch_jacobi_fast(h, P.walked(), cur, P.b, other, c.omega);
+    halo_exchange_begin(h, P, cur);
+    for (int part = 1; part <= 2; ++part) {   // interior rows while the halo is in flight, boundary rows after it has landed
+      if (part == 2) halo_exchange_end(h);
+      const int sel = h->part_overlap ? part : (part == 2 ? 0 : -1);
+      if (sel < 0) continue;
+      if (P.symmetry == B200AMG_SYMMETRY_NONE) launch_jacobi_general(h, P.A, P.diag, cur, P.b, other, c.omega, sel);
+      else launch_jacobi_fast(h, P.walked(), cur, P.b, other, c.omega, sel);
+    }
     std::swap(cur, other);
   }
   if (cur != P.x) CUDA_OK(cudaMemcpyAsync(P.x, cur, sizeof(double) * (size_t)P.plan.nloc, cudaMemcpyDeviceToDevice, h->stream));
@@ -1556,10 +1614,14 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
   NcclApi& nc = nccl_api();
   Level& L0 = *h->levels[lvl];
   smooth_part(h, P, P.pre);                                                      // :216
-  halo_exchange(h, P, P.x);
-  residual(h, P.A, P.x, P.b, P.res);                                            // :219-220
-  halo_exchange(h, P, P.res);
-  spmv(h, P.R, P.res, P.cb);                                                     // :223 (my coarse rows)
+  auto split = [&](auto&& launch) {   // interior part, join the exchange, boundary part (or everything after a blocking exchange)
+    if (h->part_overlap) { launch(1); halo_exchange_end(h); launch(2); }
+    else launch(0);
+  };
+  halo_exchange_begin(h, P, P.x);
+  split([&](int part) { residual(h, P.A, P.x, P.b, P.res, part); });               // :219-220
+  halo_exchange_begin(h, P, P.res);
+  split([&](int part) { spmv(h, P.R, P.res, P.cb, part); });                       // :223 (my coarse rows)
   if (P.child) {
     // the level below is partitioned too: the restriction wrote straight into its b (the rows I own there)
     Part& C = *P.child;
@@ -1573,8 +1635,8 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
       cycle_part_level(h, lvl + 1, B200AMG_CYCLE_F);
       cycle_part_level(h, lvl + 1, B200AMG_CYCLE_V);
     }
-    halo_exchange(h, C, C.x);                                                    // my rows of P reach into the neighbours' coarse entries
-    spmv_add(h, P.P, C.x, P.x);                                                  // :233-234
+    halo_exchange_begin(h, C, C.x);                                              // my rows of P reach into the neighbours' coarse entries
+    split([&](int part) { spmv_add(h, P.P, C.x, P.x, part); });                    // :233-234
     smooth_part(h, P, P.post);                                                   // :236
     return;
   }
@@ -1693,7 +1755,7 @@ static void sumsq_part(H* h, const double* v, double* out_dev) {
 }
 static void residual_norm_part(H* h) {   // scalars[0] = ||b - A x||^2 over all ranks
   Part& P = *h->part;
-  halo_exchange(h, P, P.x);
+  halo_exchange(h, P, P.x);   // (blocking here: the kernel below is the one bench.py times on its own)
   const bool timed = h->time_residual && h->res_events_used + 2 <= (int)h->res_events.size();
   if (timed) CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used], h->stream));
   residual(h, P.A, P.x, P.b, P.res);
@@ -1930,10 +1992,10 @@ static void build_part_level(H* h, Level& L, const HostCsr& hAt, HostCsr& hP, co
     P.plan = make_part_plan(h->rank, h->world, hA, sym ? nullptr : &hAt, hR, hP);
   const PartPlan& pl = P.plan;
   const int64_t lo = pl.row_split[pl.rank], hi = pl.row_split[pl.rank + 1];
-  P.A.upload(part_local_block(hA, lo, hi, lo, hi, pl.halo_cols));
+  P.A.upload(part_local_block(hA, lo, hi, lo, hi, pl.halo_cols), pl.nloc);
   if (sym) P.At.alias(P.A);
-  else P.At.upload(part_local_block(hAt, lo, hi, lo, hi, pl.halo_cols));
-  P.R.upload(part_local_block(hR, pl.coarse_split[pl.rank], pl.coarse_split[pl.rank + 1], lo, hi, pl.halo_cols));
+  else P.At.upload(part_local_block(hAt, lo, hi, lo, hi, pl.halo_cols), pl.nloc);
+  P.R.upload(part_local_block(hR, pl.coarse_split[pl.rank], pl.coarse_split[pl.rank + 1], lo, hi, pl.halo_cols), pl.nloc);
   {
     const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt : hA;
     std::vector<double> d((size_t)pl.nloc, 0.0);
@@ -1954,7 +2016,7 @@ static void build_part_level(H* h, Level& L, const HostCsr& hAt, HostCsr& hP, co
     parent->child = &P;
     parent->cb = P.b;
     parent->cx = P.x;
-    parent->P.upload(part_local_block(parent->pendP, pp.row_split[pp.rank], pp.row_split[pp.rank + 1], lo, hi, pl.halo_cols));
+    parent->P.upload(part_local_block(parent->pendP, pp.row_split[pp.rank], pp.row_split[pp.rank + 1], lo, hi, pl.halo_cols), pl.nloc);
     parent->pendP = HostCsr();
     parent->pendingP = false;
   }
@@ -2226,6 +2288,10 @@ int32_t b200amg_finalize(b200amg_handle_t h) {
     REQUIRE(h->part, B200AMG_ERR_STATE, "partitioned hierarchy without a fine level");
     NCCL_OK(nccl_api().CommInitRank(&h->comm, h->world, h->nccl_id, h->rank));
     h->use_graphs = false;
+    h->part_overlap = env_int("B200AMG_PART_OVERLAP", 1) != 0;
+    CUDA_OK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
   } else {
     h->x0 = dev_alloc<double>(h->n0 + 8);
     h->b0 = dev_alloc<double>(h->n0 + 8);
@@ -2245,7 +2311,16 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
     cudaFree(L->res); cudaFree(L->temp); cudaFree(L->coarse_x); cudaFree(L->coarse_b);
   }
   for (auto& pp : h->parts) pp->release();
+  // graphs that hold NCCL kernels go first: the communicator cannot be torn down while captured work still refers to it
+  for (int c = 0; c < 3; ++c) {
+    if (h->part_cycle_graph[c]) cudaGraphExecDestroy(h->part_cycle_graph[c]);
+    h->part_cycle_graph[c] = nullptr;
+  }
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   if (h->comm) nccl_api().CommDestroy(h->comm);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_done) cudaEventDestroy(h->ev_done);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
   cudaFree(h->partial); cudaFree(h->scalars); cudaFree(h->gs_fault); cudaFreeHost(h->h_scalars);

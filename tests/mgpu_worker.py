@@ -22,6 +22,8 @@ def main():
     failures = []
     cases = [("rs", (40, 40, 40), 1), ("rs", (40, 40, 40), 2), ("rs", (40, 40, 40), 3), ("sa", (96, 96), 1), ("sa", (96, 96), 2),
              ("rs", (1000,), 1), ("rs", (1000,), 4)]
+    if os.environ.get("MGPU_CASES"):          # e.g. MGPU_CASES=1,2 : a subset, for quick experiments
+        cases = [cases[int(v)] for v in os.environ["MGPU_CASES"].split(",")]
     for method, dims, plevels in cases:
         A = amg.poisson(dims if len(dims) > 1 else dims[0])
         build = amg.ruge_stuben if method == "rs" else amg.smoothed_aggregation
