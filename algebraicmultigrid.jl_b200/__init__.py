@@ -14,7 +14,7 @@ from .aggregate import StandardAggregation
 from .aggregation import JacobiProlongation, fit_candidates, smoothed_aggregation
 from .classical import direct_interpolation, ruge_stuben
 from .coarse_solver import LinearSolveWrapper, Pinv, QRSolver, UMFPACKFactorization
-from .gallery import elasticity_2d, poisson
+from .gallery import elasticity_2d, elasticity_3d, poisson
 from .multilevel import (F, Level, MultiLevel, MultiLevelWorkspace, RugeStubenAMG, SmoothedAggregationAMG, V, W,
                          _solve, _solve_, grid_complexity, init, operator_complexity, solve, solve_)
 from .preconditioner import Preconditioner, aspreconditioner, backslash, cg, ldiv_, mul_

@@ -31,7 +31,7 @@ SYMBOLS = [
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
     "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child", "b200amg_spgemm_begin", "b200amg_spgemm_fetch", "b200amg_spgemm_release",
-    "b200amg_block_plan_check",
+    "b200amg_block_plan_check", "b200amg_solve_block",
 ]
 
 
@@ -85,6 +85,7 @@ def lib():
             "b200amg_finalize": [vp],
             "b200amg_destroy": [vp],
             "b200amg_solve": [vp, vp, vp, i32, i32, dbl, dbl, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), i32],
+            "b200amg_solve_block": [vp, vp, vp, i64, i64, i32, i32, dbl, dbl, i32, vp, i32, C.POINTER(i32), C.POINTER(i32), i32],
             "b200amg_cycle": [vp, vp, vp, i32, i32],
             "b200amg_precond": [vp, vp, vp, i32, i32, i32],
             "b200amg_smooth": [vp, i32, i32, vp, vp, i32],
@@ -329,6 +330,16 @@ class DeviceHierarchy:
         nres, iters = C.c_int32(0), C.c_int32(0)
         _check(lib().b200amg_solve(self._h, _ptr(x), _ptr(b), cycle, maxiter, abstol, reltol, int(calculate_residual),
                                    _ptr(res), cap, C.byref(nres), C.byref(iters), _memkind(x)))
+        return res[: nres.value].copy(), iters.value
+
+    def solve_block(self, x, b, cycle=0, maxiter=100, abstol=0.0, reltol=1.4901161193847656e-08, calculate_residual=True):
+        """``_solve!`` for n x m blocks: ``x`` / ``b`` Fortran-ordered (column-major) float64 arrays (numpy, host)."""
+        n, m = x.shape
+        cap = int(maxiter) + 2
+        res = np.zeros(cap)
+        nres, iters = C.c_int32(0), C.c_int32(0)
+        _check(lib().b200amg_solve_block(self._h, _ptr(x), _ptr(b), m, x.strides[1] // 8, cycle, maxiter, abstol, reltol,
+                                         int(calculate_residual), _ptr(res), cap, C.byref(nres), C.byref(iters), MEM_HOST))
         return res[: nres.value].copy(), iters.value
 
     def cycle(self, x, b, cycle=0):

@@ -2396,6 +2396,70 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
   API_END
 }
 
+// _solve!(x, ml, b, ...) for MATRIX right-hand sides (the reference's block workspaces, src/multilevel.jl:28-59): x, b are
+// n x ncols, column-major with leading dimension ld (a Julia Matrix).  The reference relaxes / restricts / prolongs column by
+// column (src/smoother.jl:77,118,195; stdlib mul! over columns) and tests ONE norm over all columns (Frobenius:
+// multilevel.jl:170,190).  All columns stay on the device for the whole call: per iteration every column runs the captured
+// cycle graph on the level-0 work vectors (device-to-device copies in and out), the residual columns are formed there, and
+// only ncols sums of squares cross PCIe per iteration.
+int32_t b200amg_solve_block(b200amg_handle_t h, double* x, const double* b, int64_t ncols, int64_t ld, int32_t cycle, int32_t maxiter,
+                            double abstol, double reltol, int32_t calculate_residual, double* residuals, int32_t cap, int32_t* nres,
+                            int32_t* iters, int32_t memkind) {
+  API_BEGIN
+  check_ready(h);
+  check_not_partitioned(h, "solve_block");
+  REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
+  REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  const int64_t n = h->n0;
+  REQUIRE(ncols >= 1 && ld >= n, B200AMG_ERR_DIM_MISMATCH, "bad block shape (%lld columns, leading dimension %lld, n = %lld)",
+          (long long)ncols, (long long)ld, (long long)n);
+  const int64_t stride = (n + 8 + 1) & ~(int64_t)1;   // device column stride (16-byte aligned columns, room for the TMA slack)
+  Scratch X(stride * ncols), B(stride * ncols), SS(ncols + 8);
+  const SmootherMatrix* num = level_numbering(h, 0);
+  for (int64_t j = 0; j < ncols; ++j) {
+    vec_in(h, num, B.p + j * stride, b + j * ld, n, memkind);
+    vec_in(h, num, X.p + j * stride, x + j * ld, n, memkind);
+  }
+  std::vector<double> ss((size_t)ncols);
+  auto frobenius = [&](auto&& column) {   // sqrt of the sum over columns of ||column(j)||^2, columns added in order
+    for (int64_t j = 0; j < ncols; ++j) dot_async(h, n, column(j), column(j), SS.p + j);
+    CUDA_OK(cudaMemcpyAsync(ss.data(), SS.p, sizeof(double) * (size_t)ncols, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    double t = 0.0;
+    for (int64_t j = 0; j < ncols; ++j) t += ss[(size_t)j];
+    return std::sqrt(t);
+  };
+  int nr = 0;
+  const double normb = frobenius([&](int64_t j) { return (const double*)(B.p + j * stride); });
+  double normres = normb;                                                              // :170
+  if (normb != 0) abstol = std::max(reltol * normb, abstol);                           // :171-173
+  if (residuals && nr < cap) residuals[nr++] = normb;                                  // :174
+  const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
+  double* res = h->levels.empty() ? h->res_final : h->levels[0]->res;
+  Scratch R(calculate_residual ? stride * ncols : 1);
+  int itr = 1;
+  while (itr <= maxiter && (!calculate_residual || normres > abstol)) {                // :178
+    for (int64_t j = 0; j < ncols; ++j) {
+      CUDA_OK(cudaMemcpyAsync(h->x0, X.p + j * stride, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      CUDA_OK(cudaMemcpyAsync(h->b0, B.p + j * stride, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      run_cycle(h, cycle);                                                             // :179-183
+      CUDA_OK(cudaMemcpyAsync(X.p + j * stride, h->x0, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (calculate_residual) {
+      for (int64_t j = 0; j < ncols; ++j) residual(h, A, X.p + j * stride, B.p + j * stride, R.p + j * stride);   // :188-189
+      normres = frobenius([&](int64_t j) { return (const double*)(R.p + j * stride); });                         // :190
+      if (residuals && nr < cap) residuals[nr++] = normres;                            // :191
+    }
+    itr += 1;
+  }
+  (void)res;
+  for (int64_t j = 0; j < ncols; ++j) vec_out(h, num, x + j * ld, X.p + j * stride, n, memkind);
+  sync_and_check(h);
+  if (nres) *nres = nr;
+  if (iters) *iters = itr - 1;
+  API_END
+}
+
 int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t memkind) {
   API_BEGIN
   check_ready(h);

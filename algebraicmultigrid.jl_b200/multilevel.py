@@ -178,35 +178,20 @@ def _solve_(x, ml, b, cycle=None, *, maxiter=100, abstol=None, reltol=None, verb
 def _solve_block_(x, ml, b, cycle, n, maxiter, abstol, reltol, verbose, log, calculate_residual):
     """Matrix right-hand sides (the reference's block size > 1 workspaces, ``multilevel.jl:28-59``): the reference
     relaxes, restricts and prolongs column by column (``smoother.jl:77,118``; stdlib ``mul!`` loops over columns) and
-    tests ONE norm over all columns (Frobenius, ``multilevel.jl:170,190``).  Here every column runs the device cycle
-    (``b200amg_cycle``) and the residual columns come from ``b200amg_residual``; the vectors cross PCIe once per
-    iteration per column — functional, not a tuned path."""
+    tests ONE norm over all columns (Frobenius, ``multilevel.jl:170,190``).  ``b200amg_solve_block`` does exactly that
+    with every column resident on the device for the whole call: nothing but one sum of squares per column crosses PCIe
+    per iteration."""
     if b.shape[0] != n or np.shape(x) != b.shape:
         raise ValueError(f"DimensionMismatch: A has {n} rows, b is {b.shape}, x is {np.shape(x)}")
     dev = ml.device()
     xd = np.asfortranarray(x, dtype=np.float64)
     bd = np.asfortranarray(b, dtype=np.float64)
-    normres = normb = float(np.linalg.norm(bd))
-    if normb != 0:
-        abstol = max(reltol * normb, abstol)
-    residuals = [normb]
-    itr = 1
-    res = np.empty(n)
-    while itr <= maxiter and (not calculate_residual or normres > abstol):
-        for j in range(bd.shape[1]):
-            col = np.ascontiguousarray(xd[:, j])
-            dev.cycle(col, np.ascontiguousarray(bd[:, j]), cycle.code)
-            xd[:, j] = col
-        if calculate_residual:
-            if verbose:
-                print("Norm of residual at iteration %6d is %.4e" % (itr, normres))
-            ss = 0.0
-            for j in range(bd.shape[1]):
-                dev.residual(0 if ml.levels else len(ml.levels), res, np.ascontiguousarray(bd[:, j]), np.ascontiguousarray(xd[:, j]))
-                ss += float(res @ res)
-            normres = float(np.sqrt(ss))
-            residuals.append(normres)
-        itr += 1
+    if xd is x or np.shares_memory(xd, x):
+        xd = xd.copy(order="F")
+    residuals, iters = dev.solve_block(xd, bd, cycle.code, maxiter, abstol, reltol, bool(calculate_residual))
+    if verbose and calculate_residual:
+        for itr in range(1, iters + 1):
+            print("Norm of residual at iteration %6d is %.4e" % (itr, residuals[itr - 1]))
     x[...] = xd
     if log:
         return x, np.asarray(residuals)

@@ -165,6 +165,13 @@ int32_t b200amg_solve(b200amg_handle_t h, double* x, const double* b, int32_t cy
                       int32_t maxiter, double abstol, double reltol, int32_t calculate_residual,
                       double* residuals, int32_t cap, int32_t* nres, int32_t* iters,
                       int32_t memkind);
+/* The same for MATRIX right-hand sides (block workspaces, src/multilevel.jl:28-59; LinearSolve precs with bs > 1,
+ * src/precs.jl:12-17): x, b are n x ncols, column-major with leading dimension ld (a Julia Matrix).  Columns are relaxed /
+ * restricted / prolonged one by one (src/smoother.jl:77,118,195) and ONE Frobenius norm over all columns is tested
+ * (multilevel.jl:170,190).  Every column stays on the device for the whole call. */
+int32_t b200amg_solve_block(b200amg_handle_t h, double* x, const double* b, int64_t ncols, int64_t ld, int32_t cycle,
+                            int32_t maxiter, double abstol, double reltol, int32_t calculate_residual, double* residuals,
+                            int32_t cap, int32_t* nres, int32_t* iters, int32_t memkind);
 /* __solve!(x, ml, cycle, b, 1): exactly one cycle on the caller's x (src/multilevel.jl:214-239). */
 int32_t b200amg_cycle(b200amg_handle_t h, double* x, const double* b, int32_t cycle, int32_t memkind);
 /* ldiv!(x, p::Preconditioner, b): x .= 0 (init_zero) or x .= b, then one cycle, no residual

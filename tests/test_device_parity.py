@@ -575,6 +575,25 @@ def test_synthetic_elasticity_with_near_null_space(amg):
     ml.release()
 
 
+def test_synthetic_elasticity_3d_with_rigid_body_modes(amg):
+    # 3-D Q1 elasticity (81-entry rows, 3 dofs per node) with the six rigid-body modes as near-null-space: stand-alone solve
+    # and device PCG against the oracle, Gauss-Seidel (default) and Jacobi smoothers
+    A, b, B = amg.elasticity_3d(12, 10, 8)
+    jac = amg.Jacobi(0.5)          # (omega = 2/3 diverges as a stand-alone iteration on this operator)
+    for kw in ({}, {"presmoother": jac, "postsmoother": jac}):
+        ml = amg.smoothed_aggregation(A, B=B, **kw)
+        H = oracle.OracleHierarchy(ml)
+        x, hist = amg._solve(ml, b, log=True, reltol=1e-10, maxiter=60)
+        xr, histr = H.solve(b, log=True, reltol=1e-10, maxiter=60)
+        assert len(hist) == len(histr) and np.allclose(hist, histr, rtol=TOL_HIST)
+        assert np.linalg.norm(x - xr) <= TOL_SOLVE_X * np.linalg.norm(xr)
+        xc, info = amg.cg(A, b, Pl=amg.aspreconditioner(ml), reltol=1e-10, log=True)
+        xcr = H.pcg(b, reltol=1e-10)
+        assert info["iters"] == H.iters and np.linalg.norm(xc - xcr) <= 1e-8 * np.linalg.norm(xcr)
+        assert np.linalg.norm(A.matvec(xc) - b) <= 1e-9 * np.linalg.norm(b)
+        ml.release()
+
+
 @pytest.mark.parametrize("block", ["1", "2"])
 def test_blocked_sweep_matches_oracle(amg, fx, monkeypatch, block):
     """The blocked exact-order sweep (block_gs.cuh: one CTA per tile of rows, shared-memory window, scouts that stage far

@@ -267,3 +267,19 @@ def test_gallery(amg):
     assert np.array_equal(d, d.T) and np.all(np.diag(d) == 6)
     assert d[0, 1] == -1 and d[0, 16] == -1 and d[0, 256] == -1 and d[15, 16] == 0
     assert A.is_bitsymmetric()
+
+
+def test_elasticity_3d_generator(amg):
+    """The synthetic 3-D Q1 elasticity problem (near-null-space laid out like create_nns_frame,
+    test/nns_test.jl:138-164): symmetric positive definite, the six rigid-body modes lie in the kernel of every row that
+    does not touch the clamped face, and smoothed_aggregation(A; B=B) coarsens with six candidates per aggregate."""
+    A, b, B = amg.elasticity_3d(6, 5, 4)
+    S = A.to_scipy().toarray()
+    assert A.n == 3 * 6 * 6 * 5 and B.shape == (A.n, 6) and b.shape == (A.n,)
+    assert np.abs(S - S.T).max() <= 1e-15 and np.linalg.eigvalsh(S).min() > 0
+    free_nodes = np.nonzero(np.arange(7 * 6 * 5) % 7 != 0)[0]
+    away = np.repeat((free_nodes % 7) >= 2, 3)
+    assert np.abs(S @ B)[away].max() <= 1e-13 and np.abs(S @ B)[~away].max() > 1e-3
+    assert np.linalg.matrix_rank(B) == 6
+    ml = amg.smoothed_aggregation(A, B=B)
+    assert len(ml.levels) >= 1 and ml.levels[0].P.shape[1] % 6 == 0
