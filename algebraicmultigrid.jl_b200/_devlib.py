@@ -236,14 +236,14 @@ BLOCK_STATS = ("ok", "tiles", "stages", "steps", "lanes", "wavefronts", "mean_st
 
 
 def block_plan_check(A, x=None, b=None, omega=1.0, sor=False, sweep=3, tile_rows=0, block_a=0, block_b=0, stage_nnz=0, stage_rows=0,
-                     window=0, depth=0, verbose=0):
+                     window=0, depth=0, verbose=0, emulate_pass=False):
     """Host-only: build + validate the blocked Gauss-Seidel plan of ``A`` (``b200amg_block_plan_check``) and, when ``x`` and ``b``
-    are given, run the host emulation of the kernel's sweep.  Returns ``(stats, message, new_of_old, x_out)``."""
+    are given, run the host emulation of the kernel's sweep (``emulate_pass``: of the pass sweep, pass_gs.cuh, on the same plan).  Returns ``(stats, message, new_of_old, x_out)``."""
     import numpy as np
 
     keep = []
     d = csc_desc(A, keep)
-    params = np.array([tile_rows, block_a, block_b, stage_nnz, stage_rows, window, depth, verbose], dtype=np.int64)
+    params = np.array([tile_rows, block_a, block_b, stage_nnz, stage_rows, window, depth, verbose, int(bool(emulate_pass))], dtype=np.int64)
     stats = np.zeros(16, dtype=np.int64)
     perm = np.zeros(A.n, dtype=np.int32)
     msg = C.create_string_buffer(512)

@@ -29,6 +29,8 @@
 #include "dsm_gs.cuh"
 #include "block_plan.h"
 #include "block_gs.cuh"
+#include "pass_plan.h"
+#include "pass_gs.cuh"
 #include "spgemm.cuh"
 
 using namespace b200amg;
@@ -450,6 +452,48 @@ struct DevBlockPlan {
     ok = false;
   }
 };
+// layout of the pass sweep (pass_plan.h / pass_gs.cuh) on the device: slabs of values and per-direction codes, pass / chunk /
+// tile records; tiles, stages, requirements, ticket order and progress counters are the blocked plan's (DevBlockPlan)
+struct DevPassPlan {
+  bool ok = false;
+  int lanes = 1;
+  int64_t npasses = 0;
+  struct Dir {
+    int4* pass = nullptr;
+    int2 *tile = nullptr, *preq = nullptr, *req = nullptr;
+    double* val = nullptr;
+    int* idx = nullptr;
+  } dir[2];
+  void upload(const PassPlan& Q) {
+    lanes = Q.lanes; npasses = Q.npasses;
+    auto up4 = [](const std::vector<BI4>& v) {
+      int4* p = dev_alloc<int4>((int64_t)v.size() + 2);
+      if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(int4) * v.size(), cudaMemcpyHostToDevice));
+      return p;
+    };
+    auto up2 = [](const std::vector<BI2>& v) {
+      int2* p = dev_alloc<int2>((int64_t)v.size() + 34);
+      if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(int2) * v.size(), cudaMemcpyHostToDevice));
+      return p;
+    };
+    for (int d = 0; d < 2; ++d) {
+      const PassDir& D = Q.dir[d];
+      dir[d].tile = up2(D.tile); dir[d].pass = up4(D.pass);
+      dir[d].preq = up2(D.preq); dir[d].req = up2(D.req);
+      dir[d].val = dev_upload(D.val, 8);
+      dir[d].idx = dev_upload(D.idx, 8);
+    }
+    ok = true;
+  }
+  void release() {
+    for (int d = 0; d < 2; ++d) {
+      cudaFree(dir[d].tile); cudaFree(dir[d].pass); cudaFree(dir[d].preq); cudaFree(dir[d].req);
+      cudaFree(dir[d].val); cudaFree(dir[d].idx);
+      dir[d] = Dir();
+    }
+    ok = false;
+  }
+};
 static BlockPlanParams block_params_from_env() {
   BlockPlanParams prm;
   prm.stage_nnz = kBgStageNnz; prm.stage_rows = kBgStageRows; prm.window = kBgWindow; prm.depth = kBgDepth;
@@ -493,6 +537,7 @@ struct SmootherMatrix {
   uint4* mail = nullptr;
   unsigned* mail_ctl = nullptr;
   DevBlockPlan block;       // blocked sweep (block_gs.cuh): the default for structurally symmetric patterns
+  DevPassPlan pass;         // pass sweep (pass_gs.cuh) on the same plan
   const DevCsr& walked() const { return symmetry == B200AMG_SYMMETRY_HERMITIAN ? At : A; }
 
   // hAt_in: rows of A' (the staged CSC)
@@ -533,7 +578,16 @@ struct SmootherMatrix {
         d_new_of_old = dev_upload(perm.new_of_old);
         d_old_of_new = dev_upload(perm.old_of_new);
         block.upload(plan);
-        {
+        if (env_int("B200AMG_GS_PASS", 0) >= 1) {   // the pass sweep (pass_gs.cuh) on this plan
+          UploadTimer t_pass("pass slabs");
+          PassPlan Q = build_pass_plan(plan, symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA, kPgWinOff, kPgZeroOff);
+          if (Q.ok) pass.upload(Q);
+          if (env_int("B200AMG_BLOCK_VERBOSE", 0))
+            fprintf(stderr, "[b200amg] pass plan: %s lanes=%d passes=%lld slab entries=%lld (%.2f x nnz) requirements=%lld\n",
+                    Q.ok ? "ok" : Q.why.c_str(), Q.lanes, (long long)Q.npasses, (long long)Q.dir[0].nentries,
+                    (double)Q.dir[0].nentries / (double)std::max<int64_t>(1, plan.nnz), (long long)Q.dir[0].req.size());
+        }
+        if (!pass.ok) {
           UploadTimer t_codes("block entry codes");
           std::vector<int> cf, cb, dp;
           build_block_codes(plan, symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA, cf, cb, dp);
@@ -585,7 +639,7 @@ struct SmootherMatrix {
     for (int64_t i = 0; i < n; ++i)
       for (int k = w.ptr[i]; k < w.ptr[i + 1]; ++k)
         if (w.idx[k] == i) d[i] = w.val[k];
-    diag = dev_upload(d);
+    diag = dev_upload(d, 8);
     if (symmetry == B200AMG_SYMMETRY_NONE && (need_fwd || need_bwd)) {
       // DiagonalIndices(A): SingularException on a missing / zero diagonal  (smoother.jl:233-248)
       int64_t bad = -1;   // the reference reports the first (lowest) column without a usable diagonal
@@ -724,7 +778,7 @@ struct SmootherMatrix {
     }
   }
   void release() {
-    A.release(); At.release(); fwd.release(); bwd.release(); block.release();
+    A.release(); At.release(); fwd.release(); bwd.release(); block.release(); pass.release();
     cudaFree(diag); cudaFree(d_new_of_old); cudaFree(d_old_of_new); cudaFree(mail); cudaFree(mail_ctl); cudaFree(d_fwd_lvlptr); cudaFree(gs_meta); cudaFree(gs_tile_wave);
     cudaFree(dsm_meta); cudaFree(dsm_aux); cudaFree(dsm_status); cudaFree(dsm_code); cudaFree(dsm_rowof); cudaFree(dsm_own_off); cudaFree(dsm_wave_tiles);
     dsm_meta = nullptr; dsm_aux = nullptr; dsm_status = nullptr; dsm_code = dsm_rowof = dsm_own_off = dsm_wave_tiles = nullptr; dsm_ntiles = 0;
@@ -1274,6 +1328,33 @@ static void launch_gs_block(H* h, const SmootherMatrix& M, const DevCsr& A, cons
 #undef B200AMG_BG_CASE
   count_launch(h);
 }
+// ---- pass sweep (pass_gs.cuh) ----
+template <int T>
+static void gs_pass_set_attr() {
+  CUDA_OK(cudaFuncSetAttribute(gs_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPgSmemBytes));
+}
+static void gs_pass_kernels_init() {
+  gs_pass_set_attr<1>(); gs_pass_set_attr<2>(); gs_pass_set_attr<4>(); gs_pass_set_attr<8>(); gs_pass_set_attr<16>(); gs_pass_set_attr<32>();
+}
+static void launch_gs_pass(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
+  const DevBlockPlan& B = M.block;
+  const DevPassPlan& Q = M.pass;
+  const DevPassPlan::Dir& D = Q.dir[sc.backward ? 1 : 0];
+  CUDA_OK(cudaMemsetAsync(B.ctl, 0, sizeof(unsigned) * B.ctl_words, h->stream));
+  const int ctas = std::min(B.ntiles, h->num_sms);
+  const int* order = sc.backward ? B.order_bwd : B.order_fwd;
+#define B200AMG_PG_CASE(TT)                                                                                                                 \
+  case TT:                                                                                                                                  \
+    gs_pass_kernel<TT><<<ctas, kPgThreads, kPgSmemBytes, h->stream>>>(B.ntiles, D.tile, D.pass, D.preq, D.req, order, B.ctl, D.val, D.idx,          \
+                                                                     M.diag, x, b, w, sor, h->gs_fault, h->gs_debug);                       \
+    break;
+  switch (Q.lanes) {
+    B200AMG_PG_CASE(1) B200AMG_PG_CASE(2) B200AMG_PG_CASE(4) B200AMG_PG_CASE(8) B200AMG_PG_CASE(16) B200AMG_PG_CASE(32)
+    default: REQUIRE(false, B200AMG_ERR_STATE, "pass sweep: unsupported lane count %d", Q.lanes);
+  }
+#undef B200AMG_PG_CASE
+  count_launch(h);
+}
 constexpr int64_t kGsCtaXsRows = 12288;   // x of the level fits next to the tile ring in shared memory
 template <int T, bool XS>
 static void gs_cta_set_attr() {
@@ -1315,6 +1396,7 @@ static void launch_gs_cta(H* h, const SmootherMatrix& M, const DevCsr& A, const 
 }
 static void launch_sweep(H* h, const SmootherMatrix& M, const DevSchedule& sc, double* x, const double* b, double w, int sor) {
   const DevCsr& A = M.walked();
+  if (M.pass.ok) { launch_gs_pass(h, M, sc, x, b, w, sor); return; }
   if (M.block.ok) { launch_gs_block(h, M, A, sc, x, b, w, sor); return; }
   if (h->gs_mode >= 1 && h->gs_dsm && M.d_fwd_lvlptr && M.dsm_ntiles > 0 && M.dsm_log_nc <= h->gs_dsm_max_log_nc &&
       !(sc.nlev > 0 && M.n / sc.nlev >= h->gs_mail_min_width)) {
@@ -1932,6 +2014,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   gs_cta_kernels_init();
   dsm_kernels_init();
   gs_block_kernels_init();
+  gs_pass_kernels_init();
   CUDA_OK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   gs_tile_ctas<1>(); gs_tile_ctas<2>(); gs_tile_ctas<4>(); gs_tile_ctas<8>(); gs_tile_ctas<16>(); gs_tile_ctas<32>();
   h->stream_chunk = env_int("B200AMG_STREAM_CHUNK", 4);
@@ -2254,8 +2337,42 @@ int32_t b200amg_block_plan_check(const b200amg_csc_t* A, const int64_t* params, 
     const int64_t n = w.nrows;
     std::vector<double> xp((size_t)n), bp((size_t)n);
     for (int64_t q = 0; q < n; ++q) { xp[q] = x[P.perm.old_of_new[q]]; bp[q] = b[P.perm.old_of_new[q]]; }
-    if (sweep == 1 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, false);
-    if (sweep == 2 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, true);
+    if (params && params[8] == 1) {   // the pass sweep's layout and addressing rules (pass_plan.h) on the same plan
+      PassPlan Q = build_pass_plan(P, wp, kPgWinOff, kPgZeroOff);
+      if (!Q.ok) {
+        stats[0] = -2;
+        if (msg && msg_cap > 0) snprintf(msg, (size_t)msg_cap, "pass plan: %s", Q.why.c_str());
+        return B200AMG_OK;
+      }
+      std::vector<double> dg((size_t)n, 0.0);
+      for (int64_t q = 0; q < n; ++q)
+        for (int k = wp.ptr[q]; k < wp.ptr[q + 1]; ++k)
+          if (wp.idx[k] == q) dg[(size_t)q] = wp.val[k];
+      std::string e2;
+      if (sweep == 1 || sweep == 3) e2 = emulate_pass_sweep(P, Q, wp, xp, bp, dg, omega, sor != 0, false, kPgWinOff, kPgZeroOff);
+      if (e2.empty() && (sweep == 2 || sweep == 3)) e2 = emulate_pass_sweep(P, Q, wp, xp, bp, dg, omega, sor != 0, true, kPgWinOff, kPgZeroOff);
+      if (!e2.empty()) {
+        stats[0] = -3;
+        if (msg && msg_cap > 0) snprintf(msg, (size_t)msg_cap, "pass emulation: %s", e2.c_str());
+      }
+      stats[4] = Q.lanes; stats[2] = 0; stats[3] = Q.npasses;
+      stats[12] = (int64_t)Q.dir[0].req.size(); stats[13] = (int64_t)Q.dir[1].req.size();
+      if (prm.verbose) {   // timing model of the schedule: where a sweep's time would go
+        const double tp = env_int("B200AMG_MODEL_TPASS_NS", 250) * 1e-3;
+        const int ncs[3] = {148, 148, 100000};
+        const double lams[3] = {1.5, 0.0, 1.5};
+        for (int q = 0; q < 3; ++q) {
+          double busy = 0, wf = 0;
+          const double us = simulate_pass_sweep(P, Q, false, ncs[q], tp, lams[q], 3.0, 2, &busy, &wf);
+          fprintf(stderr, "[b200amg] pass model: n=%lld lanes=%d tiles=%d passes=%lld wavefronts=%d | CTAs %d lam %.1f t_pass %.2f us -> forward sweep %.1f us "
+                  "(%.2f us per wavefront), CTAs busy %.0f %%, mean wait before a tile's first pass %.1f us\n", (long long)P.n, Q.lanes, P.ntiles,
+                  (long long)Q.npasses, P.global_wavefronts, ncs[q], lams[q], tp, us, us / std::max(1, P.global_wavefronts), 100.0 * busy, wf);
+        }
+      }
+    } else {
+      if (sweep == 1 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, false);
+      if (sweep == 2 || sweep == 3) emulate_block_sweep(P, wp, xp, bp, omega, sor != 0, true);
+    }
     for (int64_t q = 0; q < n; ++q) x_out[P.perm.old_of_new[q]] = xp[q];
   }
   API_END
@@ -2894,7 +3011,8 @@ int32_t b200amg_debug_gs_timeline(b200amg_handle_t h, int32_t level, int32_t bac
     h->gs_debug = d;
     double* xb = level == 0 ? h->x0 : h->levels[level - 1]->coarse_x;
     const double* bb = level == 0 ? h->b0 : h->levels[level - 1]->coarse_b;
-    launch_gs_block(h, L.M, L.M.walked(), sc, xb, bb, L.pre.omega, L.pre.kind == B200AMG_SMOOTHER_SOR);
+    if (L.M.pass.ok) launch_gs_pass(h, L.M, sc, xb, bb, L.pre.omega, L.pre.kind == B200AMG_SMOOTHER_SOR);
+    else launch_gs_block(h, L.M, L.M.walked(), sc, xb, bb, L.pre.omega, L.pre.kind == B200AMG_SMOOTHER_SOR);
     h->gs_debug = nullptr;
     CUDA_OK(cudaMemcpyAsync(out, d, sizeof(unsigned long long) * (size_t)words, cudaMemcpyDeviceToHost, h->stream));
     CUDA_OK(cudaStreamSynchronize(h->stream));

@@ -145,7 +145,9 @@ int32_t b200amg_partition_plan_child(const b200amg_csc_t* A, const b200amg_csc_t
  * every invariant the kernel relies on, and optionally EXECUTED by the host emulation of the kernel: x_out = the sweep(s)
  * `sweep` (1 forward, 2 backward, 3 symmetric) applied to x with right-hand side b (all in the caller's numbering).
  * params (may be NULL; 0 = default): [0] contiguous tile rows, [1] block a, [2] block b, [3] stage entries, [4] stage rows,
- * [5] window, [6] depth, [7] verbose.  stats[16]: [0] 1 ok / 0 not applicable / -1 invariant violated (msg says which),
+ * [5] window, [6] depth, [7] verbose, [8] 1: emulate the PASS sweep (csrc/device/pass_plan.h, pass_gs.cuh: slabs, near / far
+ * codes, window) on the same plan instead (stats[0] -2: no pass layout, -3: its addressing rules violated; [2] / [3] / [4] then
+ * report chunks / passes / lanes of the pass layout).  params holds 9 entries.  stats[16]: [0] 1 ok / 0 not applicable / -1 invariant violated (msg says which),
  * [1] tiles, [2] stages, [3] steps, [4] lanes per row, [5] wavefronts of the whole level, [6] 1000 x mean rows per step,
  * [7] theta, [8] a, [9] b, [10] rows of the largest tile, [11] steps of the longest tile, [12] / [13] forward / backward
  * requirements, [14] / [15] extents of the K / J coordinates.  new_of_old (may be NULL): n entries. */

@@ -19,6 +19,11 @@ def _check(amg, A, sm, **kw):
     assert sorted(perm.tolist()) == list(range(A.n))
     ref = oracle.smooth(A, sm, x.copy(), b)
     assert np.abs(xo - ref).max() <= 1e-13 * np.abs(ref).max()
+    # the pass sweep's layout (pass_plan.h: slabs, near / far codes, window, look-ahead rules) on the same plan
+    st2, msg2, _, xo2 = _devlib.block_plan_check(A, x, b, omega=getattr(sm, "omega", 1.0), sor=sm.kind == "sor", sweep=sweep,
+                                                 emulate_pass=True, **kw)
+    assert st2["ok"] == 1, msg2
+    assert np.abs(xo2 - ref).max() <= 1e-13 * np.abs(ref).max()
     return st
 
 

@@ -594,12 +594,15 @@ def test_synthetic_elasticity_3d_with_rigid_body_modes(amg):
         ml.release()
 
 
-@pytest.mark.parametrize("block", ["1", "2"])
+@pytest.mark.parametrize("block", ["1", "2", "pass"])
 def test_blocked_sweep_matches_oracle(amg, fx, monkeypatch, block):
     """The blocked exact-order sweep (block_gs.cuh: one CTA per tile of rows, shared-memory window, scouts that stage far
     values, cross-tile progress counters) against the reference's sequential sweeps: Gauss-Seidel and SOR, forward /
     backward / symmetric, on stencils of every dimension, irregular RS coarse operators, a finite-element matrix and
     multi-tile levels; B200AMG_GS_BLOCK=2 forces it onto every level of a hierarchy, =1 is the default per-level choice."""
+    if block == "pass":      # the pass sweep (pass_gs.cuh) on every level's blocked plan
+        monkeypatch.setenv("B200AMG_GS_PASS", "1")
+        block = "2"
     monkeypatch.setenv("B200AMG_GS_BLOCK", block)
     ml0 = amg.ruge_stuben(amg.poisson((40, 40, 40)))
     mats = [amg.poisson(777), amg.poisson((40, 33)), amg.poisson((20, 17, 12)), amg.poisson((40, 40, 40)), fx.matrix("thing")]
