@@ -31,7 +31,7 @@ SYMBOLS = [
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
     "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child", "b200amg_spgemm_begin", "b200amg_spgemm_fetch", "b200amg_spgemm_release",
-    "b200amg_block_plan_check", "b200amg_solve_block",
+    "b200amg_block_plan_check", "b200amg_solve_block", "b200amg_comm_stats",
 ]
 
 
@@ -120,6 +120,8 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = i32
+        L.b200amg_comm_stats.argtypes = [vp, vp, i32]
+        L.b200amg_comm_stats.restype = i32
         L.b200amg_launch_count.argtypes = [vp]
         L.b200amg_launch_count.restype = i64
         _lib = L
@@ -389,6 +391,11 @@ class DeviceHierarchy:
 
     def launch_count(self):
         return int(lib().b200amg_launch_count(self._h))
+
+    def comm_stats(self):
+        out = np.zeros(4, dtype=np.int64)
+        _check(lib().b200amg_comm_stats(self._h, out.ctypes.data, 4))
+        return {"nccl_groups": int(out[0]), "peer_exchanges": int(out[1]), "peer_halo": bool(out[2]), "partitioned_levels": int(out[3])}
 
     def time_kernel(self, level, what, cycle=0, reps=20, flush_l2=False):
         ms = C.c_double(0)

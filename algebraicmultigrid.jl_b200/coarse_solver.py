@@ -9,6 +9,18 @@ from __future__ import annotations
 import numpy as np
 
 
+DENSE_LIMIT = 16384   # rows: the device applies the coarse solve as ONE dense operator (b200amg_set_coarse, include/b200amg.h)
+
+
+def _check_dense_limit(A, who):
+    """The reference keeps a sparse factorisation of the coarsest matrix (``coarse_solver.jl:66-81``) and works for any size;
+    here the host forms a dense n x n operator that the device applies, so a coarsest level beyond DENSE_LIMIT rows (coarsening
+    stopped early: ``max_levels`` reached, an empty ``P``) is refused with a clear message instead of exhausting memory."""
+    if A.m > DENSE_LIMIT:
+        raise ValueError(f"{who}: the coarsest matrix has {A.m} rows; the dense coarse operator is limited to {DENSE_LIMIT} "
+                         "(raise max_levels / lower max_coarse so that coarsening continues)")
+
+
 class CoarseSolver:
     def dense_operator(self):
         raise NotImplementedError
@@ -18,6 +30,7 @@ class Pinv(CoarseSolver):
     """Moore-Penrose pseudo-inverse (``coarse_solver.jl:9-16``)."""
 
     def __init__(self, A):
+        _check_dense_limit(A, "Pinv")
         self.pinvA = np.linalg.pinv(A.todense()) if A.n else np.zeros((0, 0))
 
     def dense_operator(self):
@@ -34,6 +47,7 @@ class QRSolver(CoarseSolver):
     solution) the minimum-norm operator ``pinv(A)`` is used instead — documented deviation."""
 
     def __init__(self, A):
+        _check_dense_limit(A, "QRSolver")
         a = A.todense()
         n = a.shape[0]
         if n == 0:
@@ -60,6 +74,7 @@ class LinearSolveWrapperInternal(CoarseSolver):
         import scipy.sparse.linalg as spl
 
         self.alg = alg
+        _check_dense_limit(A, "LinearSolveWrapper")
         lu = spl.splu(A.to_scipy().tocsc())
         self.op = lu.solve(np.eye(A.n)) if A.n else np.zeros((0, 0))
 

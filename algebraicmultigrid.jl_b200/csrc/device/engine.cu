@@ -31,6 +31,7 @@
 #include "block_gs.cuh"
 #include "pass_plan.h"
 #include "pass_gs.cuh"
+#include "peer_halo.cuh"
 #include "spgemm.cuh"
 
 using namespace b200amg;
@@ -98,6 +99,7 @@ struct NcclApi {
   decltype(&ncclRecv) Recv = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   bool ok = false;
 };
 static NcclApi& nccl_api() {
@@ -120,6 +122,7 @@ static NcclApi& nccl_api() {
   B200AMG_NCCL_SYM(Recv, "ncclRecv")
   B200AMG_NCCL_SYM(AllReduce, "ncclAllReduce")
   B200AMG_NCCL_SYM(Broadcast, "ncclBroadcast")
+  B200AMG_NCCL_SYM(AllGather, "ncclAllGather")
 #undef B200AMG_NCCL_SYM
   api.ok = true;
   return api;
@@ -905,6 +908,18 @@ struct b200amg_hierarchy {
   bool capturing = false;
   int64_t launches = 0;       // kernels launched (graph replays add their node counts)
   int64_t collectives = 0;    // NCCL groups / collectives enqueued (partitioned handles)
+  // halo exchange over peer memory (peer_halo.cuh): on when every rank could map its neighbours' vectors
+  struct PeerCtx {
+    bool on = false;
+    unsigned long long* sync = nullptr;   // my flag / ack / counter words (exported)
+    unsigned* tickets = nullptr;          // one per (level, channel)
+    PeerTables* d_tab = nullptr;          // [levels * channels]
+    std::vector<void*> opened;            // peer mappings to close
+  } peer;
+  Part* peer_pending = nullptr;           // the exchange whose halo has not been acknowledged yet
+  int peer_pending_ch = 0;
+  int64_t peer_exchanges = 0;
+  int64_t part_cycle_peer[3] = {0, 0, 0};
   int64_t capture_count = 0;  // kernels recorded into the graph being captured
   // staging for renumbered vectors crossing the ABI
   double* io_tmp = nullptr;
@@ -1623,8 +1638,34 @@ __global__ void __launch_bounds__(kThreads) halo_pack_kernel(int n, const int* _
 }
 
 // v is laid out [owned | halo]: gather what the neighbours need, exchange, receive straight into the halo
+static int peer_channel(const Part& P, const double* v) { return v == P.x ? 0 : v == P.temp ? 1 : v == P.res ? 2 : -1; }
+// the kernel(s) that read the halo of the last exchange have been enqueued on the compute stream: tell the senders
+static void halo_consumed(H* h) {
+  if (!h->peer_pending) return;
+  const int slot = h->peer_pending->level * kPeerChannels + h->peer_pending_ch;
+  halo_ack_kernel<<<1, 32, 0, h->stream>>>(h->peer.d_tab + slot, h->peer.sync + (size_t)slot * kPeerWords);
+  count_launch(h);
+  h->peer_pending = nullptr;
+}
 static void halo_exchange(H* h, Part& P, double* v) {
   const PartPlan& pl = P.plan;
+  if (h->peer.on) {
+    const int ch = peer_channel(P, v);
+    REQUIRE(ch >= 0, B200AMG_ERR_STATE, "peer halo exchange of a vector that was not exported");
+    REQUIRE(!h->peer_pending, B200AMG_ERR_STATE, "internal: a halo exchange was started before the previous one was acknowledged");
+    const int slot = P.level * kPeerChannels + ch;
+    unsigned long long* sync = h->peer.sync + (size_t)slot * kPeerWords;
+    const int nsend = pl.send_off[pl.world];
+    const int blocks = std::max(1, std::min(64, (nsend + 255) / 256));
+    halo_push_kernel<<<blocks, 256, 0, h->stream>>>(h->peer.d_tab + slot, P.send_idx, v, sync, h->peer.tickets + slot, h->gs_fault);
+    count_launch(h);
+    halo_wait_kernel<<<1, 32, 0, h->stream>>>(h->peer.d_tab + slot, sync, h->gs_fault);
+    count_launch(h);
+    h->peer_pending = &P;
+    h->peer_pending_ch = ch;
+    h->peer_exchanges++;
+    return;
+  }
   NcclApi& nc = nccl_api();
   const int nsend = pl.send_off[pl.world];
   if (nsend > 0) {
@@ -1667,7 +1708,8 @@ static void halo_exchange_end(H* h) {
 
 static void smooth_part(H* h, Part& P, const SmootherCfg& c) {
   if (c.kind == B200AMG_SMOOTHER_NONE || P.plan.nloc == 0) {
-    if (c.kind != B200AMG_SMOOTHER_NONE) for (int it = 0; it < c.iter; ++it) halo_exchange(h, P, P.x);   // keep the collectives matched
+    if (c.kind != B200AMG_SMOOTHER_NONE)
+      for (int it = 0; it < c.iter; ++it) { halo_exchange(h, P, P.x); halo_consumed(h); }   // keep the exchanges matched
     return;
   }
   double* cur = P.x;
@@ -1681,6 +1723,7 @@ static void smooth_part(H* h, Part& P, const SmootherCfg& c) {
       if (P.symmetry == B200AMG_SYMMETRY_NONE) launch_jacobi_general(h, P.A, P.diag, cur, P.b, other, c.omega, sel);
       else launch_jacobi_fast(h, P.walked(), cur, P.b, other, c.omega, sel);
     }
+    halo_consumed(h);
     std::swap(cur, other);
   }
   if (cur != P.x) CUDA_OK(cudaMemcpyAsync(P.x, cur, sizeof(double) * (size_t)P.plan.nloc, cudaMemcpyDeviceToDevice, h->stream));
@@ -1699,6 +1742,7 @@ static void cycle_part_level(H* h, int lvl, int cycle) {
   auto split = [&](auto&& launch) {   // interior part, join the exchange, boundary part (or everything after a blocking exchange)
     if (h->part_overlap) { launch(1); halo_exchange_end(h); launch(2); }
     else launch(0);
+    halo_consumed(h);
   };
   halo_exchange_begin(h, P, P.x);
   split([&](int part) { residual(h, P.A, P.x, P.b, P.res, part); });               // :219-220
@@ -1797,7 +1841,7 @@ static void cycle_body_part(H* h, int cycle) {
   if (!h->part_whole_graph || h->profiling) { cycle_part_level(h, 0, cycle); return; }
   if (!h->part_cycle_graph[cycle]) {
     cudaGraph_t g = nullptr;
-    const int64_t coll0 = h->collectives;
+    const int64_t coll0 = h->collectives, peer0 = h->peer_exchanges;
     h->capturing = true;
     h->capture_count = 0;
     CUDA_OK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -1816,10 +1860,13 @@ static void cycle_body_part(H* h, int cycle) {
     h->part_cycle_launches[cycle] = h->capture_count;
     h->part_cycle_collectives[cycle] = h->collectives - coll0;
     h->collectives = coll0;
+    h->part_cycle_peer[cycle] = h->peer_exchanges - peer0;
+    h->peer_exchanges = peer0;
   }
   CUDA_OK(cudaGraphLaunch(h->part_cycle_graph[cycle], h->stream));
   h->launches += h->part_cycle_launches[cycle];
   h->collectives += h->part_cycle_collectives[cycle];
+  h->peer_exchanges += h->part_cycle_peer[cycle];
 }
 
 // sum over ranks of a device scalar, in place; every rank gets the same bits
@@ -1845,6 +1892,7 @@ static void residual_norm_part(H* h) {   // scalars[0] = ||b - A x||^2 over all 
     CUDA_OK(cudaEventRecord(h->res_events[h->res_events_used + 1], h->stream));
     h->res_events_used += 2;
   }
+  halo_consumed(h);
   sumsq_part(h, P.res, h->scalars);
 }
 // owned slice in, assembled vector out
@@ -2394,6 +2442,103 @@ int32_t b200amg_partition_info(b200amg_handle_t h, int64_t* row_lo, int64_t* row
   API_END
 }
 
+// Export my exchangeable vectors and flag words, map the neighbours' (CUDA IPC over NVLink), build the per-channel tables of
+// peer_halo.cuh.  Collective: every rank calls it at finalize; the path is switched on only if EVERY rank succeeded.
+struct PeerBlob {
+  cudaIpcMemHandle_t sync;
+  cudaIpcMemHandle_t buf[kPeerMaxLevels][kPeerChannels];
+  int recv_off[kPeerMaxLevels][kPeerMaxWorld + 1];
+  long long nloc[kPeerMaxLevels];
+  int ok;
+};
+static void peer_setup(H* h) {
+  const int world = h->world, me = h->rank, nl = (int)h->parts.size();
+  int ok = env_int("B200AMG_PEER_HALO", 1) != 0 && world <= kPeerMaxWorld && nl <= kPeerMaxLevels;
+  std::vector<PeerBlob> all((size_t)world);
+  PeerBlob mine;
+  memset(&mine, 0, sizeof mine);
+  h->peer.sync = dev_alloc<unsigned long long>(kPeerSyncWords);
+  CUDA_OK(cudaMemset(h->peer.sync, 0, sizeof(unsigned long long) * kPeerSyncWords));
+  h->peer.tickets = dev_alloc<unsigned>(kPeerMaxLevels * kPeerChannels);
+  CUDA_OK(cudaMemset(h->peer.tickets, 0, sizeof(unsigned) * kPeerMaxLevels * kPeerChannels));
+  if (ok) {
+    ok = cudaIpcGetMemHandle(&mine.sync, h->peer.sync) == cudaSuccess;
+    for (int l = 0; l < nl && ok; ++l) {
+      Part& P = *h->parts[(size_t)l];
+      double* bufs[kPeerChannels] = {P.x, P.temp, P.res};
+      for (int c = 0; c < kPeerChannels && ok; ++c) ok = cudaIpcGetMemHandle(&mine.buf[l][c], bufs[c]) == cudaSuccess;
+      for (int q = 0; q <= world; ++q) mine.recv_off[l][q] = P.plan.recv_off[(size_t)q];
+      mine.nloc[l] = P.plan.nloc;
+    }
+    (void)cudaGetLastError();
+  }
+  mine.ok = ok;
+  {   // all-gather of the blobs (bytes) over the communicator that already exists
+    unsigned char* d_all = dev_alloc<unsigned char>((int64_t)sizeof(PeerBlob) * world);
+    CUDA_OK(cudaMemcpy(d_all + sizeof(PeerBlob) * (size_t)me, &mine, sizeof mine, cudaMemcpyHostToDevice));
+    NCCL_OK(nccl_api().AllGather(d_all + sizeof(PeerBlob) * (size_t)me, d_all, sizeof(PeerBlob), ncclChar, h->comm, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpy(all.data(), d_all, sizeof(PeerBlob) * (size_t)world, cudaMemcpyDeviceToHost));
+    cudaFree(d_all);
+  }
+  for (int q = 0; q < world; ++q) ok = ok && all[(size_t)q].ok;
+  std::vector<PeerTables> tabs((size_t)(kPeerMaxLevels * kPeerChannels));
+  memset(tabs.data(), 0, sizeof(PeerTables) * tabs.size());
+  if (ok) {
+    std::vector<unsigned long long*> rsync((size_t)world, nullptr);
+    auto open = [&](const cudaIpcMemHandle_t& hd) -> void* {
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { (void)cudaGetLastError(); ok = 0; return nullptr; }
+      h->peer.opened.push_back(p);
+      return p;
+    };
+    for (int l = 0; l < nl && ok; ++l) {
+      const PartPlan& pl = h->parts[(size_t)l]->plan;
+      for (int q = 0; q < world && ok; ++q) {
+        if (q == me) continue;
+        const bool sends = pl.send_off[(size_t)q + 1] > pl.send_off[(size_t)q], recvs = pl.recv_off[(size_t)q + 1] > pl.recv_off[(size_t)q];
+        if (!sends && !recvs) continue;
+        if (!rsync[(size_t)q]) rsync[(size_t)q] = (unsigned long long*)open(all[(size_t)q].sync);
+        if (!ok) break;
+        for (int c = 0; c < kPeerChannels && ok; ++c) {
+          PeerTables& T = tabs[(size_t)(l * kPeerChannels + c)];
+          unsigned long long* words = rsync[(size_t)q] + (size_t)(l * kPeerChannels + c) * kPeerWords;
+          T.flag_at[q] = words + me;
+          T.ack_at[q] = words + kPeerMaxWorld + me;
+          if (sends) {
+            double* base = (double*)open(all[(size_t)q].buf[l][c]);
+            if (!ok) break;
+            T.dst[q] = base + all[(size_t)q].nloc[l] + all[(size_t)q].recv_off[l][me];
+            // what I send must be exactly what q expects from me
+            if (all[(size_t)q].recv_off[l][me + 1] - all[(size_t)q].recv_off[l][me] != pl.send_off[(size_t)q + 1] - pl.send_off[(size_t)q]) ok = 0;
+          }
+        }
+      }
+      for (int c = 0; c < kPeerChannels; ++c) {
+        PeerTables& T = tabs[(size_t)(l * kPeerChannels + c)];
+        T.world = world;
+        for (int q = 0; q <= world; ++q) T.send_off[q] = pl.send_off[(size_t)q];
+        for (int q = 0; q < world; ++q) T.recv_cnt[q] = pl.recv_off[(size_t)q + 1] - pl.recv_off[(size_t)q];
+      }
+    }
+  }
+  {   // agree: all ranks or none
+    int* d_ok = dev_alloc<int>(2);
+    CUDA_OK(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+    NCCL_OK(nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, h->comm, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    CUDA_OK(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_ok);
+  }
+  if (ok) {
+    h->peer.d_tab = dev_alloc<PeerTables>((int64_t)tabs.size());
+    CUDA_OK(cudaMemcpy(h->peer.d_tab, tabs.data(), sizeof(PeerTables) * tabs.size(), cudaMemcpyHostToDevice));
+  }
+  h->peer.on = ok != 0;
+  if (env_int("B200AMG_VERBOSE_UPLOAD", 0) || env_int("B200AMG_PEER_VERBOSE", 0))
+    fprintf(stderr, "[b200amg] rank %d: halo exchange over %s\n", me, h->peer.on ? "peer memory (CUDA IPC, direct stores into the neighbours' halos)" : "NCCL send/recv");
+}
+
 int32_t b200amg_finalize(b200amg_handle_t h) {
   API_BEGIN
   REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
@@ -2409,6 +2554,7 @@ int32_t b200amg_finalize(b200amg_handle_t h) {
     CUDA_OK(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    peer_setup(h);
   } else {
     h->x0 = dev_alloc<double>(h->n0 + 8);
     h->b0 = dev_alloc<double>(h->n0 + 8);
@@ -2434,6 +2580,9 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
     h->part_cycle_graph[c] = nullptr;
   }
   if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
+  for (void* p : h->peer.opened) cudaIpcCloseMemHandle(p);
+  h->peer.opened.clear();
+  cudaFree(h->peer.sync); cudaFree(h->peer.tickets); cudaFree(h->peer.d_tab);
   if (h->comm) nccl_api().CommDestroy(h->comm);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -2846,6 +2995,18 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
 
 int64_t b200amg_launch_count(b200amg_handle_t h) { return h ? h->launches : 0; }
 
+// counters of a partitioned handle: [0] NCCL groups / collectives enqueued so far, [1] halo exchanges over peer memory so far,
+// [2] 1 if the halo exchanges go over peer memory (CUDA IPC), 0 if over NCCL send/recv, [3] partitioned levels
+int32_t b200amg_comm_stats(b200amg_handle_t h, int64_t* out, int32_t cap) {
+  API_BEGIN
+  REQUIRE(h && out && cap >= 4, B200AMG_ERR_BAD_ARG, "bad argument");
+  out[0] = h->collectives;
+  out[1] = h->peer_exchanges;
+  out[2] = h->peer.on ? 1 : 0;
+  out[3] = (int64_t)h->parts.size();
+  API_END
+}
+
 int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int32_t cycle, int32_t reps, int32_t flush_l2,
                             double* ms) {
   API_BEGIN
@@ -2880,7 +3041,7 @@ int32_t b200amg_time_kernel(b200amg_handle_t h, int32_t level, int32_t what, int
         case 3: spmv(h, P.R, P.res, P.cb); break;
         case 4: spmv_add(h, P.P, P.cx, P.x); break;
         case 6: sumsq_part(h, P.b, h->scalars + 4); break;
-        case 7: halo_exchange(h, P, P.x); break;
+        case 7: halo_exchange(h, P, P.x); halo_consumed(h); break;
         default: REQUIRE(false, B200AMG_ERR_BAD_ARG, "unknown kernel selector %d", what);
       }
     } else if (what == 6) {

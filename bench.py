@@ -333,12 +333,14 @@ def run_ours(args):
     barrier()
     sampler.start()
     launches0 = dev.launch_count()
+    comm0 = dev.comm_stats() if world > 1 else None
     e0.record(stream)
     hist, iters = dev.solve(x_d, b_d, 0, K, 0.0, 0.0, True)
     e1.record(stream)
     barrier()
     clocks = sampler.stop()
     launches = dev.launch_count() - launches0
+    comm1 = dev.comm_stats() if world > 1 else None
     ms = e0.elapsed_time(e1)
     res_ms = dev.residual_timings()
     dev.set_option(1, 0)
@@ -500,7 +502,14 @@ def run_ours(args):
         line["note"] = ("BASELINE config C4: Jacobi smoother (Gauss-Seidel, the N=1 headline config C3, is sequential over the "
                         "index range and does not shard); the finest --part-levels levels are split by rows, the levels below them run "
                         "on rank 0, which bounds the whole-cycle speed-up (Amdahl); strong-scaling baseline = n1_same_workload")
-        line["nccl_collectives_in_timed_region"] = None
+        line["comm"] = {"halo_exchange": "peer memory: every rank maps its neighbours' vectors (CUDA IPC) and stores its boundary entries straight "
+                                         "into their halos over NVLink, flag + ack words instead of a rendezvous (csrc/device/peer_halo.cuh)"
+                                         if comm1["peer_halo"] else "NCCL grouped send/recv",
+                        "peer_halo_exchanges_per_step": (comm1["peer_exchanges"] - comm0["peer_exchanges"]) / K,
+                        "nccl_groups_per_step": (comm1["nccl_groups"] - comm0["nccl_groups"]) / K,
+                        "nccl_groups_what": "coarse_b rows -> rank 0, coarse_x windows <- rank 0, one all-reduce of the squared residual norm",
+                        "partitioned_levels": comm1["partitioned_levels"], "one_halo_exchange_ms": halo_ms}
+        roofline["comm"] = line["comm"]
     if world == 1 and not args.no_other_configs:
         line["other_configs"] = other_configs(amg, torch, local)
     line.update(extra)

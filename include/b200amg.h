@@ -218,6 +218,10 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
                            int64_t* nnz_p, int64_t* wavefronts);
 /* kernels launched by this handle since creation (graph replays count their kernel nodes). */
 int64_t b200amg_launch_count(b200amg_handle_t h);
+/* Communication counters of a row-partitioned handle (cap >= 4): [0] NCCL groups / collectives enqueued so far, [1] halo
+ * exchanges done over peer memory so far, [2] 1 if halo exchanges use peer memory (CUDA IPC mappings of the neighbours'
+ * vectors, direct NVLink stores: csrc/device/peer_halo.cuh), 0 if NCCL send/recv, [3] partitioned levels. */
+int32_t b200amg_comm_stats(b200amg_handle_t h, int64_t* out, int32_t cap);
 /* Time `reps` back-to-back launches of one hot-path kernel on the handle's stream with CUDA
  * events; returns the average milliseconds per launch in *ms.  what: 0 spmv y=A x, 1 residual,
  * 2 pre-smoother, 3 restriction, 4 prolongation+correction, 5 one full cycle, 6 norm,

@@ -20,11 +20,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     jac = amg.Jacobi(2.0 / 3.0)
     failures = []
-    cases = [("rs", (40, 40, 40), 1), ("rs", (40, 40, 40), 2), ("rs", (40, 40, 40), 3), ("sa", (96, 96), 1), ("sa", (96, 96), 2),
-             ("rs", (1000,), 1), ("rs", (1000,), 4)]
+    # (method, grid, partitioned levels, halo exchange over peer memory [csrc/device/peer_halo.cuh] or over NCCL send / recv)
+    cases = [("rs", (40, 40, 40), 1, 1), ("rs", (40, 40, 40), 2, 1), ("rs", (40, 40, 40), 3, 1), ("rs", (40, 40, 40), 3, 0), ("sa", (96, 96), 1, 1),
+             ("sa", (96, 96), 2, 1), ("sa", (96, 96), 2, 0), ("rs", (1000,), 1, 1), ("rs", (1000,), 4, 1)]
     if os.environ.get("MGPU_CASES"):          # e.g. MGPU_CASES=1,2 : a subset, for quick experiments
         cases = [cases[int(v)] for v in os.environ["MGPU_CASES"].split(",")]
-    for method, dims, plevels in cases:
+    for method, dims, plevels, peer in cases:
+        os.environ["B200AMG_PEER_HALO"] = str(peer)      # read when the hierarchy is finalized on the device
         A = amg.poisson(dims if len(dims) > 1 else dims[0])
         build = amg.ruge_stuben if method == "rs" else amg.smoothed_aggregation
         ml = build(A, presmoother=jac, postsmoother=jac)
@@ -48,7 +50,7 @@ def main():
                 e = np.linalg.norm(x - xr) / np.linalg.norm(xr)
                 ep = np.abs(p - H.precond(b, cycle=cname)).max() / np.abs(r1).max()
                 ok = e1 < 1e-11 and e < 1e-9 and ep < 1e-11 and len(hist) == len(histr) and np.allclose(hist, histr, rtol=1e-6) and same
-                print(f"[mgpu] {method} {dims} part_levels={plevels} {cname}: cycle {e1:.1e} solve {e:.1e} precond {ep:.1e} iters {len(hist) - 1}/{len(histr) - 1} "
+                print(f"[mgpu] {method} {dims} part_levels={plevels} {'peer' if ml.device().comm_stats()['peer_halo'] else 'nccl'} {cname}: cycle {e1:.1e} solve {e:.1e} precond {ep:.1e} iters {len(hist) - 1}/{len(histr) - 1} "
                       f"same_on_all_ranks={same} {'OK' if ok else 'FAIL'}", flush=True)
                 if not ok:
                     failures.append((method, dims, plevels, cname))
