@@ -31,7 +31,7 @@ SYMBOLS = [
     "b200amg_time_kernel", "b200amg_profile_cycle", "b200amg_device_vectors", "b200amg_set_option",
     "b200amg_residual_timings", "b200amg_get_stream", "b200amg_debug_gs_timeline", "b200amg_nccl_unique_id",
     "b200amg_partition_info", "b200amg_partition_plan", "b200amg_partition_plan_child", "b200amg_spgemm_begin", "b200amg_spgemm_fetch", "b200amg_spgemm_release",
-    "b200amg_block_plan_check", "b200amg_solve_block", "b200amg_comm_stats",
+    "b200amg_block_plan_check", "b200amg_solve_block", "b200amg_comm_stats", "b200amg_storage_info",
 ]
 
 
@@ -120,6 +120,8 @@ def lib():
             fn = getattr(L, name)
             fn.argtypes = args
             fn.restype = i32
+        L.b200amg_storage_info.argtypes = [vp, i32, vp, i32]
+        L.b200amg_storage_info.restype = i32
         L.b200amg_comm_stats.argtypes = [vp, vp, i32]
         L.b200amg_comm_stats.restype = i32
         L.b200amg_launch_count.argtypes = [vp]
@@ -391,6 +393,12 @@ class DeviceHierarchy:
 
     def launch_count(self):
         return int(lib().b200amg_launch_count(self._h))
+
+    def storage_info(self, level):
+        """Bytes per stored matrix value the bandwidth kernels read on ``level``: ``{"A": 4 | 8, "P": .., "R": ..}``."""
+        out = np.zeros(3, dtype=np.int32)
+        _check(lib().b200amg_storage_info(self._h, level, out.ctypes.data, 3))
+        return {"A": int(out[0]), "P": int(out[1]), "R": int(out[2])}
 
     def comm_stats(self):
         out = np.zeros(4, dtype=np.int64)

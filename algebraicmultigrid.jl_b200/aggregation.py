@@ -60,7 +60,8 @@ def smoothed_aggregation(A, bs=1, *, B=None, symmetry=None, strength=None, aggre
     assert A.m == B.shape[0]
     levels = []
     bsr_flag = False
-    w = MultiLevelWorkspace(bs, A.nzval.dtype)
+    eltype = getattr(A, "eltype", np.dtype(np.float64))
+    w = MultiLevelWorkspace(bs, eltype)
     residual_(w, A.m)
     while len(levels) + 1 < max_levels and A.m > max_coarse:
         A, B, bsr_flag, stop = extend_hierarchy_sa_(levels, strength, aggregate, smooth, improve_candidates,
@@ -95,8 +96,13 @@ def extend_hierarchy_sa_(levels, strength, aggregate, smooth, improve_candidates
     P = smooth(A, T, S, B)
     if P.n == 0:
         return A, B, True, True
+    f32 = getattr(A, "eltype", np.dtype(np.float64)) == np.float32     # a Float32 hierarchy holds Float32 operators on every level
+    if f32:
+        P = P.astype(np.float32)
     R = construct_R(symmetry, P)
     RAP = _hostlib.spgemm(_hostlib.spgemm(P.transpose(), A), P)      # (R*A)*P
+    if f32:
+        RAP = RAP.astype(np.float32)
     pre = setup_smoother(presmoother, A, symmetry)
     post = setup_smoother(postsmoother, A, symmetry)
     levels.append(Level(A, P, R, pre, post))

@@ -29,7 +29,8 @@ def ruge_stuben(A, bs=1, *, strength=None, symmetry=None, CF=None, presmoother=N
         raise RuntimeError("near null space `B` is only supported for smoothed aggregation AMG, not Ruge-Stüben AMG.")
 
     levels = []
-    w = MultiLevelWorkspace(bs, A.nzval.dtype)
+    eltype = getattr(A, "eltype", np.dtype(np.float64))
+    w = MultiLevelWorkspace(bs, eltype)
     residual_(w, A.m)
     while len(levels) + 1 < max_levels and A.m > max_coarse:
         A, stop = extend_hierarchy_rs_(levels, strength, CF, A, presmoother, postsmoother, symmetry)
@@ -43,6 +44,16 @@ def ruge_stuben(A, bs=1, *, strength=None, symmetry=None, CF=None, presmoother=N
     return MultiLevel(levels, A, cs, presmoother, postsmoother, w)
 
 
+def _as_eltype(M, A):
+    """A hierarchy built from a Float32 matrix holds Float32 operators on every level (the reference computes them in Float32;
+    here they are computed in fp64 and rounded once): keeps ``eltype(ml)`` and lets the device store them with 4-byte values."""
+    if getattr(A, "eltype", np.dtype(np.float64)) != np.float32:
+        return M
+    if isinstance(M, Adjoint):
+        return Adjoint(M.parent.astype(np.float32))
+    return M.astype(np.float32)
+
+
 def extend_hierarchy_rs_(levels, strength, CF, A, presmoother, postsmoother, symmetry):
     """``extend_hierarchy_rs!`` (``classical.jl:36-55``)."""
     At = A if isinstance(symmetry, HermitianSymmetry) else A.transpose()
@@ -51,11 +62,14 @@ def extend_hierarchy_rs_(levels, strength, CF, A, presmoother, postsmoother, sym
     P, R = direct_interpolation(At, T, splitting)
     if P.shape[1] == 0:
         return A, True
+    if getattr(A, "eltype", np.dtype(np.float64)) == np.float32:
+        R = _as_eltype(R, A)
+        P = Adjoint(R) if isinstance(P, Adjoint) else _as_eltype(P, A)
     RAP = _hostlib.spgemm(_hostlib.spgemm(R, A), R.transpose())      # (R*A)*P, structural zeros kept
     pre = setup_smoother(presmoother, A, symmetry)
     post = setup_smoother(postsmoother, A, symmetry)
     levels.append(Level(A, P, R, pre, post))
-    return RAP, False
+    return _as_eltype(RAP, A), False
 
 
 def direct_interpolation(At, T, splitting):

@@ -245,6 +245,8 @@ struct DevCsr {
   int* ptr = nullptr;
   int* idx = nullptr;
   double* val = nullptr;
+  float* val32 = nullptr;   // the same values in binary32 when EVERY one of them is exactly representable (else nullptr): the
+                            // stream kernels then read 8 instead of 12 bytes per entry and compute the same fp64 products
   int lanes = 8;  // lanes per row of the vector kernels
   // tile plan of the TMA stream kernels (stream.cuh); ntiles == 0: not streamable (a row > kTileNnz)
   int4* meta = nullptr;
@@ -264,6 +266,18 @@ struct DevCsr {
     idx = dev_upload(h.idx, 8);
     val = dev_upload(h.val, 8);
     owner = true;
+    if (env_int("B200AMG_FP32_STORAGE", 0) && nnz > 0) {   // lossless narrow storage (opt-in: see H::fp32_storage)
+      bool exact = true;
+      const int64_t nz = nnz;
+#pragma omp parallel for schedule(static) reduction(&& : exact)
+      for (int64_t k = 0; k < nz; ++k) exact = exact && ((double)(float)h.val[(size_t)k] == h.val[(size_t)k]);
+      if (exact) {
+        std::vector<float> v32((size_t)nz);
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < nz; ++k) v32[(size_t)k] = (float)h.val[(size_t)k];
+        val32 = dev_upload(v32, 16);
+      }
+    }
     const double mean = nrows ? (double)nnz / (double)nrows : 0.0;
     lanes = 2;
     while (lanes < 32 && lanes < mean) lanes *= 2;
@@ -311,8 +325,8 @@ struct DevCsr {
   }
   void alias(const DevCsr& o) { *this = o; owner = false; }
   void release() {
-    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(meta); cudaFree(meta_split); }
-    ptr = idx = nullptr; val = nullptr; meta = nullptr; meta_split = nullptr; ntiles = ntiles_int = ntiles_bnd = 0; owner = false;
+    if (owner) { cudaFree(ptr); cudaFree(idx); cudaFree(val); cudaFree(val32); cudaFree(meta); cudaFree(meta_split); }
+    ptr = idx = nullptr; val = nullptr; val32 = nullptr; meta = nullptr; meta_split = nullptr; ntiles = ntiles_int = ntiles_bnd = 0; owner = false;
   }
 };
 
@@ -907,6 +921,11 @@ struct b200amg_hierarchy {
   bool finalized = false;
   bool capturing = false;
   int64_t launches = 0;       // kernels launched (graph replays add their node counts)
+  // stream kernels read the binary32 copy of an operator's values where one exists (DevCsr::val32).  OFF by default: measured on
+  // B200 (256^3 fine level, profiles/r02_fp32_storage_ab.md) the residual takes 0.392 ms with 4-byte values against 0.347 ms
+  // with 8-byte values — the kernel is co-limited by instruction issue, and seven F2F.F64.F32 conversions per row (quarter
+  // rate) plus shorter bulk copies cost more than the 25 % fewer bytes save.  B200AMG_FP32_STORAGE=1 / B200AMG_OPT_FP32_STORAGE.
+  bool fp32_storage = env_int("B200AMG_FP32_STORAGE", 0) != 0;
   int64_t collectives = 0;    // NCCL groups / collectives enqueued (partitioned handles)
   // halo exchange over peer memory (peer_halo.cuh): on when every rank could map its neighbours' vectors
   struct PeerCtx {
@@ -952,11 +971,14 @@ static inline unsigned grid_for(int64_t work_items) {
 template <int T, int MODE>
 static void stream_set_attr() {
   CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<T, MODE, kStreamBurst, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
 }
 template <int MODE>
 static void stream_set_attr_all() {
   CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<2, MODE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
   CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<4, MODE, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<2, MODE, 16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+  CUDA_OK(cudaFuncSetAttribute(csr_stream_kernel<4, MODE, 16, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
   stream_set_attr<1, MODE>(); stream_set_attr<2, MODE>(); stream_set_attr<4, MODE>();
   stream_set_attr<8, MODE>(); stream_set_attr<16, MODE>(); stream_set_attr<32, MODE>();
 }
@@ -964,6 +986,33 @@ static void stream_kernels_init() {   // once per device context: opt in to 86 K
   stream_set_attr_all<0>(); stream_set_attr_all<1>(); stream_set_attr_all<2>(); stream_set_attr_all<3>(); stream_set_attr_all<4>();
 }
 // part: 0 every tile, 1 the interior tiles, 2 the boundary tiles (row-partitioned levels, DevCsr::meta_split)
+template <int MODE, typename VT>
+static void launch_stream_vt(H* h, const DevCsr& A, const VT* val, int ctas, int chunk, const double* x, const double* b, double* y,
+                             double omega, const double* diagvals) {
+#define B200AMG_STREAM_CASE(TT)                                                                                                        \
+  case TT:                                                                                                                             \
+    csr_stream_kernel<TT, MODE, kStreamBurst, VT><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, \
+                                                                                                        val, x, b, y, omega, diagvals); \
+    break;
+  if (A.stream_burst == 16) {   // 13-64 entries per row: two / four lanes, one burst of 16 gathers each
+    if (A.stream_lanes == 2)
+      csr_stream_kernel<2, MODE, 16, VT><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, val, x, b, y,
+                                                                                               omega, diagvals);
+    else
+      csr_stream_kernel<4, MODE, 16, VT><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, val, x, b, y,
+                                                                                               omega, diagvals);
+    count_launch(h);
+    return;
+  }
+  switch (A.stream_lanes) {
+    B200AMG_STREAM_CASE(1) B200AMG_STREAM_CASE(2) B200AMG_STREAM_CASE(4) B200AMG_STREAM_CASE(8) B200AMG_STREAM_CASE(16)
+    default:
+      csr_stream_kernel<32, MODE, kStreamBurst, VT><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, val,
+                                                                                                          x, b, y, omega, diagvals);
+  }
+#undef B200AMG_STREAM_CASE
+  count_launch(h);
+}
 template <int MODE>
 static void launch_stream(H* h, const DevCsr& A0, const double* x, const double* b, double* y, double omega,
                           const double* diagvals, int part = 0) {
@@ -973,30 +1022,9 @@ static void launch_stream(H* h, const DevCsr& A0, const double* x, const double*
   else if (part == 2) { A.meta = A0.meta_split + A0.ntiles_int; A.ntiles = A0.ntiles_bnd; }
   if (A.ntiles == 0) return;
   const int ctas = std::min(A.ntiles, h->num_sms * 2);
-  int chunk = h->stream_chunk > 0 ? h->stream_chunk : (A.ntiles + ctas - 1) / ctas;
-#define B200AMG_STREAM_CASE(TT)                                                                                         \
-  case TT:                                                                                                              \
-    csr_stream_kernel<TT, MODE><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, \
-                                                                                      A.val, x, b, y, omega, diagvals); \
-    break;
-  if (A.stream_burst == 16) {   // 13-64 entries per row: two / four lanes, one burst of 16 gathers each
-    if (A.stream_lanes == 2)
-      csr_stream_kernel<2, MODE, 16><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, A.val,
-                                                                                           x, b, y, omega, diagvals);
-    else
-      csr_stream_kernel<4, MODE, 16><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx, A.val,
-                                                                                           x, b, y, omega, diagvals);
-    count_launch(h);
-    return;
-  }
-  switch (A.stream_lanes) {
-    B200AMG_STREAM_CASE(1) B200AMG_STREAM_CASE(2) B200AMG_STREAM_CASE(4) B200AMG_STREAM_CASE(8) B200AMG_STREAM_CASE(16)
-    default:
-      csr_stream_kernel<32, MODE><<<ctas, kStreamThreads, kStreamSmemBytes, h->stream>>>(A.ntiles, chunk, A.meta, A.ptr, A.idx,
-                                                                                        A.val, x, b, y, omega, diagvals);
-  }
-#undef B200AMG_STREAM_CASE
-  count_launch(h);
+  const int chunk = h->stream_chunk > 0 ? h->stream_chunk : (A.ntiles + ctas - 1) / ctas;
+  if (A.val32 && h->fp32_storage) launch_stream_vt<MODE, float>(h, A, A.val32, ctas, chunk, x, b, y, omega, diagvals);
+  else launch_stream_vt<MODE, double>(h, A, A.val, ctas, chunk, x, b, y, omega, diagvals);
 }
 
 template <int MODE>
@@ -2993,6 +3021,27 @@ int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_
   API_END
 }
 
+// bytes per stored VALUE the bandwidth kernels read on a level: out[0] A, out[1] P, out[2] R (4 = the lossless binary32 copy is
+// in use, 8 = fp64; 0 = the operator does not exist on this rank)
+int32_t b200amg_storage_info(b200amg_handle_t h, int32_t level, int32_t* out, int32_t cap) {
+  API_BEGIN
+  REQUIRE(h && out && cap >= 3, B200AMG_ERR_BAD_ARG, "bad argument");
+  const int nl = (int)h->levels.size();
+  REQUIRE(level >= 0 && level <= nl, B200AMG_ERR_BAD_ARG, "level %d out of range", level);
+  auto vb = [&](const DevCsr& M) { return M.nnz == 0 && !M.val ? 0 : (M.val32 && h->fp32_storage ? 4 : 8); };
+  out[0] = out[1] = out[2] = 0;
+  if (level == nl) {
+    out[0] = vb(h->finalA);
+  } else if (level < (int)h->parts.size()) {
+    const Part& P = *h->parts[(size_t)level];
+    out[0] = vb(P.A); out[1] = vb(P.P); out[2] = vb(P.R);
+  } else {
+    const Level& L = *h->levels[(size_t)level];
+    out[0] = vb(L.M.A); out[1] = vb(L.P); out[2] = vb(L.R);
+  }
+  API_END
+}
+
 int64_t b200amg_launch_count(b200amg_handle_t h) { return h ? h->launches : 0; }
 
 // counters of a partitioned handle: [0] NCCL groups / collectives enqueued so far, [1] halo exchanges over peer memory so far,
@@ -3128,6 +3177,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_DSM: h->gs_dsm = (int)value; break;
     case B200AMG_OPT_GS_DSM_FENCE: h->gs_dsm_fence = (int)value; break;
     case B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2: h->gs_dsm_max_log_nc = (int)value; break;
+    case B200AMG_OPT_FP32_STORAGE: h->fp32_storage = value != 0; break;
     case 16: h->gs_poll_masked = (int)value; break;   // experiment knob (tools/tune_kernels.py)
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");

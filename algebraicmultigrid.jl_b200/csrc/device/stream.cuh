@@ -31,12 +31,17 @@ constexpr int kTileRowsMax = 1024;
 constexpr int kStages = 3;
 constexpr int kStreamBurst = 8;   // x gathers a lane issues back to back for a short row (template default)
 
-struct __align__(16) StreamStage {
-  double val[kTileNnz + 8];
+// VT: how the matrix values are STORED (double, or float when every value of the operator is exactly representable in
+// binary32 — decided at upload, DevCsr::val32 — so that the products, computed in fp64 either way, are bit-identical: 8
+// instead of 12 bytes per entry cross HBM)
+template <typename VT>
+struct __align__(16) StreamStageT {
+  VT val[kTileNnz + 8];
   int col[kTileNnz + 8];
   int rp[kTileRowsMax + 8];
 };
-static_assert(sizeof(StreamStage) % 16 == 0, "stage must keep 16-byte alignment");
+using StreamStage = StreamStageT<double>;
+static_assert(sizeof(StreamStage) % 16 == 0 && sizeof(StreamStageT<float>) % 16 == 0, "stage must keep 16-byte alignment");
 constexpr int kStreamSmemBytes = kStages * (int)sizeof(StreamStage);
 
 // ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------
@@ -68,13 +73,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
-__device__ __forceinline__ void stream_issue(StreamStage& S, uint64_t* bar, const int4 m, const int* __restrict__ rowptr,
-                                             const int* __restrict__ col, const double* __restrict__ val) {
+template <typename VT>
+__device__ __forceinline__ void stream_issue(StreamStageT<VT>& S, uint64_t* bar, const int4 m, const int* __restrict__ rowptr,
+                                             const int* __restrict__ col, const VT* __restrict__ val) {
   const int ka = m.z & ~3, kcnt = (m.w - ka + 3) & ~3;
   const int ra = m.x & ~3, rcnt = (m.y + 1 - ra + 3) & ~3;
-  mbar_expect_tx(bar, (uint32_t)(kcnt * 12 + rcnt * 4));
+  mbar_expect_tx(bar, (uint32_t)(kcnt * (4 + (int)sizeof(VT)) + rcnt * 4));
   if (kcnt) {
-    bulk_g2s(S.val, val + ka, (uint32_t)kcnt * 8u, bar);
+    bulk_g2s(S.val, val + ka, (uint32_t)kcnt * (uint32_t)sizeof(VT), bar);
     bulk_g2s(S.col, col + ka, (uint32_t)kcnt * 4u, bar);
   }
   bulk_g2s(S.rp, rowptr + ra, (uint32_t)rcnt * 4u, bar);
@@ -92,14 +98,14 @@ __device__ __forceinline__ int stream_tile_of(int i, int chunk) {
   return (i / chunk) * ((int)gridDim.x * chunk) + (int)blockIdx.x * chunk + (i % chunk);
 }
 
-template <int T, int MODE, int BURST = kStreamBurst>
+template <int T, int MODE, int BURST = kStreamBurst, typename VT = double>
 __global__ void __launch_bounds__(kStreamThreads, 2)
     csr_stream_kernel(int ntiles, int chunk, const int4* __restrict__ meta, const int* __restrict__ rowptr,
-                      const int* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                      const int* __restrict__ col, const VT* __restrict__ val, const double* __restrict__ x,
                       const double* __restrict__ b, double* __restrict__ y, double omega,
                       const double* __restrict__ diagvals) {
   extern __shared__ __align__(128) unsigned char stream_smem[];
-  StreamStage* st = reinterpret_cast<StreamStage*>(stream_smem);
+  StreamStageT<VT>* st = reinterpret_cast<StreamStageT<VT>*>(stream_smem);
   __shared__ __align__(8) uint64_t full[kStages];
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
         if (MODE == 4) pre_d[q] = __ldg(diagvals + row);
       }
     mbar_wait(&full[s], parity);
-    const StreamStage& S = st[s];
+    const StreamStageT<VT>& S = st[s];
     for (int rbase = 0; rbase < nrows; rbase += G) {
       const int r = rbase + g;
       double sum = 0.0, diag = 0.0;
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
             const int k = ks + lane + j * T;
             const bool in = k < ke;
             c[j] = in ? S.col[k] : -1;
-            v[j] = in ? S.val[k] : 0.0;
+            v[j] = in ? (double)S.val[k] : 0.0;
           }
 #pragma unroll
           for (int j = 0; j < BURST; ++j) {
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(kStreamThreads, 2)
 #pragma unroll 4
           for (int k = ks + lane; k < ke; k += T) {
             const int c = S.col[k];
-            const double v = S.val[k];
+            const double v = (double)S.val[k];
             if (MODE == 3) {
               if (c == row) diag = v;
               else sum = __dadd_rn(sum, __dmul_rn(v, __ldg(x + c)));

@@ -18,13 +18,19 @@ IDX = np.int32
 class SparseMatrixCSC:
     """m x n sparse matrix: ``colptr`` (n+1), ``rowval`` (nnz, sorted per column), ``nzval`` (nnz)."""
 
-    __slots__ = ("m", "n", "colptr", "rowval", "nzval", "_bitsym")
+    __slots__ = ("m", "n", "colptr", "rowval", "nzval", "_bitsym", "eltype")
 
-    def __init__(self, m, n, colptr, rowval, nzval):
+    def __init__(self, m, n, colptr, rowval, nzval, eltype=None):
         self.m = int(m)
         self.n = int(n)
         self.colptr = np.ascontiguousarray(colptr, dtype=IDX)
         self.rowval = np.ascontiguousarray(rowval, dtype=IDX)
+        # ``eltype``: the element type the caller's matrix has (Float32 or Float64, test/runtests.jl:244-259).  The values are
+        # always HELD as float64 (a Float32 matrix holds binary32-representable numbers; host setup and device kernels compute
+        # in fp64, the device stores such operators with 4-byte values: B200AMG_OPT_FP32_STORAGE)
+        if eltype is None:
+            eltype = np.float32 if getattr(nzval, "dtype", None) == np.float32 else np.float64
+        self.eltype = np.dtype(eltype)
         self.nzval = np.ascontiguousarray(nzval, dtype=np.float64)
         if self.colptr.shape[0] != self.n + 1:
             raise ValueError("colptr must have n+1 entries")
@@ -77,7 +83,13 @@ class SparseMatrixCSC:
         return self.shape if d is None else self.shape[d - 1]
 
     def copy(self):
-        return SparseMatrixCSC(self.m, self.n, self.colptr.copy(), self.rowval.copy(), self.nzval.copy())
+        return SparseMatrixCSC(self.m, self.n, self.colptr.copy(), self.rowval.copy(), self.nzval.copy(), self.eltype)
+
+    def astype(self, eltype):
+        """``T.(A)``: the same pattern with the values rounded to ``eltype`` (``np.float32`` / ``np.float64``)."""
+        eltype = np.dtype(eltype)
+        vals = self.nzval.astype(np.float32).astype(np.float64) if eltype == np.float32 else self.nzval.copy()
+        return SparseMatrixCSC(self.m, self.n, self.colptr.copy(), self.rowval.copy(), vals, eltype)
 
     def to_scipy(self):
         import scipy.sparse as sp

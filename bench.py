@@ -136,12 +136,31 @@ def bench_config(args, A, nlevels):
     return {"workload": workload_name(args), "n": A.n, "nnz": A.nnz, "levels": nlevels}
 
 
-def bytes_spmv(n, nnz):       # fp64 values, int32 column indices + row pointers, x counted once
-    return 12 * nnz + 4 * (n + 1) + 16 * n
+def bytes_spmv(n, nnz, vb=8):       # values (vb bytes each: 8 = fp64, 4 = the lossless binary32 copy), int32 column
+    return (vb + 4) * nnz + 4 * (n + 1) + 16 * n      # indices + row pointers, x counted once
 
 
-def bytes_residual(n, nnz):
-    return 12 * nnz + 4 * (n + 1) + 24 * n
+def bytes_residual(n, nnz, vb=8):   # also one Jacobi sweep, one Gauss-Seidel direction
+    return (vb + 4) * nnz + 4 * (n + 1) + 24 * n
+
+
+def cycle_bytes(infos, stor, smoother):
+    """Algorithmic bytes of ONE `_solve!` iteration (V-cycle + convergence residual) over the whole hierarchy, with the value
+    width every level is actually stored in: per level (pre + post sweeps) x sweep + residual + restriction + prolongation
+    (SURVEY §8d); Gauss-Seidel sweeps read the fp64 values (their kernels have no binary32 path)."""
+    tot = 0
+    sweeps = 4 if smoother == "gs" else 2          # symmetric GS = 2 directions pre + 2 post; Jacobi 1 + 1
+    for i, (lv, st) in enumerate(zip(infos, stor)):
+        if lv["nnz_p"] == 0 and i == len(infos) - 1:
+            continue                                # the coarsest matrix: dense solve
+        n, nnz, nc = lv["n"], lv["nnz_a"], infos[i + 1]["n"] if i + 1 < len(infos) else 0
+        vb_s = 8 if smoother == "gs" else (st["A"] or 8)
+        tot += sweeps * bytes_residual(n, nnz, vb_s) + bytes_residual(n, nnz, st["A"] or 8)
+        tot += ((st["R"] or 8) + 4) * lv["nnz_p"] + 4 * (nc + 1) + 8 * n + 8 * nc
+        tot += ((st["P"] or 8) + 4) * lv["nnz_p"] + 4 * (n + 1) + 8 * nc + 16 * n
+    if infos:
+        tot += bytes_residual(infos[0]["n"], infos[0]["nnz_a"], stor[0]["A"] or 8)      # the convergence residual
+    return tot
 
 
 def run_reference(args):
@@ -239,8 +258,9 @@ def other_configs(amg, torch, local):
                      "levels": dev.nlevels, "setup_s": t_setup,
                      "iters_per_s_l2_resident": 1e3 / hot, "ms_per_iter_l2_resident": hot,
                      "iters_per_s_l2_flushed": 1e3 / cold, "ms_per_iter_l2_flushed": cold,
-                     "fine_spmv_gbs_l2_resident": bytes_spmv(A.n, A.nnz) / (spmv_hot * 1e-3) / 1e9,
-                     "fine_spmv_gbs_l2_flushed": bytes_spmv(A.n, A.nnz) / (spmv_cold * 1e-3) / 1e9,
+                     "fine_spmv_gbs_l2_resident": bytes_spmv(A.n, A.nnz, dev.storage_info(0)["A"] or 8) / (spmv_hot * 1e-3) / 1e9,
+                     "fine_spmv_gbs_l2_flushed": bytes_spmv(A.n, A.nnz, dev.storage_info(0)["A"] or 8) / (spmv_cold * 1e-3) / 1e9,
+                     "fine_value_bytes": dev.storage_info(0)["A"],
                      "l2": "the whole hierarchy (0.09 GB) fits the 126 MB L2: the resident figures are L2 rates; flushed = a 512 MB "
                            "write before every single-iteration call (launch-latency-bound: ~60 kernels of 5-30 us)"}
         ml.release()
@@ -274,6 +294,36 @@ def other_configs(amg, torch, local):
         ml.release()
     except Exception as exc:
         out["C5"] = {"error": str(exc)[:300]}
+    try:                                   # ---- synthetic 3-D elasticity (north_star: "synthetic Poisson / elasticity matrices")
+        t0 = time.time()
+        A, bvec, B = amg.elasticity_3d(40, 40, 40)
+        t_gen = time.time() - t0
+        res = {}
+        for name, kw in (("gauss_seidel", {}), ("jacobi_0.5", {"presmoother": amg.Jacobi(0.5), "postsmoother": amg.Jacobi(0.5)})):
+            t0 = time.time()
+            ml = amg.smoothed_aggregation(A, B=B, **kw)
+            t_setup = time.time() - t0
+            dev = ml.device()
+            b = torch.from_numpy(bvec).to(dev_t)
+            x = torch.zeros(A.n, dtype=torch.float64, device=dev_t)
+            hist, iters = dev.pcg(x, b, 0, 300, 0.0, 1e-8)       # warm-up (captures the cycle graph)
+            x.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hist, iters = dev.pcg(x, b, 0, 300, 0.0, 1e-8)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            xh = x.cpu().numpy()
+            res[name] = {"levels": dev.nlevels, "setup_s": t_setup, "cg_iterations": int(iters), "solve_ms": 1e3 * dt,
+                         "cg_iterations_per_s": iters / dt,
+                         "relative_residual": float(np.linalg.norm(A.matvec(xh) - bvec) / np.linalg.norm(bvec)),
+                         "fine_spmv_gbs_l2_flushed": bytes_spmv(A.n, A.nnz, dev.storage_info(0)["A"] or 8) / (dev.time_kernel(0, 0, reps=10, flush_l2=True) * 1e-3) / 1e9}
+            ml.release()
+        out["elasticity_3d"] = {"workload": "elasticity_3d(40,40,40): Q1 hexahedra, 3 dofs per node, clamped face, smoothed_aggregation with the six "
+                                            "rigid-body modes as near-null-space, device-resident CG preconditioned by one V-cycle, reltol 1e-8",
+                                "n": A.n, "nnz": A.nnz, "generate_s": t_gen, "smoothers": res}
+    except Exception as exc:
+        out["elasticity_3d"] = {"error": str(exc)[:300]}
     del flush
     return out
 
@@ -410,31 +460,66 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
         return
-    # ---- roofline of the headline kernel: fine-level residual SpMV r = b - A x ------------------------
+    # ---- the BASELINE metric's kernel: fine-level residual SpMV r = b - A x, timed live inside every timed iteration ----
     peak, peak_src = measured_peak()
     res_ms_avg = float(np.mean(res_ms)) if len(res_ms) else float("nan")
-    alg = bytes_residual(n // world, nnz // world) if world > 1 else bytes_residual(n, nnz)
+    stor = [dev.storage_info(i) for i in range(dev.nlevels)]
+    vb0 = stor[0]["A"] or 8
+    alg = bytes_residual(n // world, nnz // world, vb0) if world > 1 else bytes_residual(n, nnz, vb0)
     achieved = alg / (res_ms_avg * 1e-3) / 1e9
-    roofline = {"kernel": "csr residual r=b-A*x, fine level (convergence check of every `_solve!` iteration)",
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
-                "avg_launch_ms": res_ms_avg, "launches_timed": int(len(res_ms)), "share_of_step": res_ms_avg / (ms / K),
-                "traffic": ncu_traffic(args, world),
-                "traffic_source": "static: one `ncu --set full` capture of this kernel on this workload, committed as "
-                                  "profiles/r01_ncu_traffic.json (not measured in this run)"}
+    traffic = ncu_traffic(args, world) if vb0 == 8 else None
+    spmv_roofline = {"kernel": "csr residual r=b-A*x, fine level (convergence check of every `_solve!` iteration)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "algorithmic_bytes": alg,
+                     "value_bytes": vb0,
+                     "value_bytes_note": ("the fine-level values are exactly representable in binary32 and are stored (also) as 4-byte values; "
+                                          "the kernel computes the same fp64 products (bit-identical results), so the algorithmic bytes are "
+                                          "8 per entry, not SURVEY §8d's 12" if vb0 == 4 else "fp64 values: 12 bytes per entry (SURVEY §8d)"),
+                     "fp64_storage_equivalent_gbs": bytes_residual(n // world, nnz // world) / (res_ms_avg * 1e-3) / 1e9,
+                     "avg_launch_ms": res_ms_avg, "launches_timed": int(len(res_ms)), "share_of_step": res_ms_avg / (ms / K),
+                     "traffic": traffic,
+                     "traffic_source": "static: one `ncu --set full` capture of the fp64-storage kernel on this workload, committed as "
+                                       "profiles/r01_ncu_traffic.json (not measured in this run; null for the binary32-storage kernel)"}
     phases = ["presmoother", "residual", "restriction", "coarse_solve", "prolongation", "postsmoother"]
     prof = dev.profile_cycle(0) if world == 1 else np.zeros((dev.nlevels, 6))
     infos = [dev.level_info(i) for i in range(dev.nlevels)]
+    # ---- `roofline` = the DOMINANT kernel of the step (largest share of the step time), and the whole step ----
+    step_alg = cycle_bytes(infos, stor, args.smoother)
+    whole_step = {"algorithmic_bytes": step_alg, "achieved": step_alg / (ms / K * 1e-3) / 1e9 * (1 if world == 1 else 1), "unit": "GB/s",
+                  "frac": step_alg / (ms / K * 1e-3) / 1e9 / (peak * world), "peak": peak * world,
+                  "what": "all kernels of one `_solve!` iteration over the whole hierarchy against the measured HBM peak of the GPUs used"}
+    roofline = dict(spmv_roofline)
+    if world == 1 and prof.size:
+        sm_ms = prof[:, 0] + prof[:, 5]                    # pre + post smoother per level
+        other = np.array([prof[:, 1].max(), prof[:, 2].max(), prof[:, 4].max()])
+        li = int(np.argmax(sm_ms))
+        if sm_ms[li] / 2 > other.max():                    # a smoother sweep dominates (always, for Gauss-Seidel)
+            lv = infos[li]
+            launches_per_step = 4 if args.smoother == "gs" else 2
+            k_ms = float(sm_ms[li]) / launches_per_step
+            k_alg = bytes_residual(lv["n"], lv["nnz_a"], 8 if args.smoother == "gs" else (stor[li]["A"] or 8))
+            k_ach = k_alg / (k_ms * 1e-3) / 1e9
+            what = ("exact-order Gauss-Seidel sweep (one direction; gs! src/smoother.jl:73-90) of level %d: %d rows, %d dependent wavefronts — "
+                    "dependency-latency-bound, not bandwidth-bound" % (li, lv["n"], lv["wavefronts"])) if args.smoother == "gs" else \
+                   ("Jacobi sweep of level %d (%d rows)" % (li, lv["n"]))
+            roofline = {"kernel": what, "bound": "hbm", "achieved": k_ach, "peak": peak, "unit": "GB/s", "frac": k_ach / peak,
+                        "peak_source": peak_src, "algorithmic_bytes": k_alg, "avg_launch_ms": k_ms,
+                        "launches_per_step": launches_per_step, "share_of_step": float(sm_ms[li]) / (ms / K),
+                        "how_timed": "CUDA events around each phase of one cycle replayed eagerly (b200amg_profile_cycle), after the timed region",
+                        "traffic": None}
+    roofline["whole_step"] = whole_step
+    roofline["fine_level_residual_spmv"] = spmv_roofline
     pinfo = dev.partition_info() if world > 1 else None
     nl, nnzl = (pinfo["row_hi"] - pinfo["row_lo"], nnz // world) if world > 1 else (n, nnz)
     extra = {
-        "fine_spmv_ms": spmv_ms, "fine_spmv_gbs": bytes_spmv(nl, nnzl) / (spmv_ms * 1e-3) / 1e9,
-        "fine_spmv_frac_of_measured_peak": bytes_spmv(nl, nnzl) / (spmv_ms * 1e-3) / 1e9 / peak,
+        "fine_spmv_ms": spmv_ms, "fine_spmv_gbs": bytes_spmv(nl, nnzl, vb0) / (spmv_ms * 1e-3) / 1e9,
+        "fine_spmv_frac_of_measured_peak": bytes_spmv(nl, nnzl, vb0) / (spmv_ms * 1e-3) / 1e9 / peak,
+        "fine_spmv_value_bytes": vb0,
         "fine_spmv_note": "rank 0's row block, local kernel only" if world > 1 else "whole fine level",
         "fine_presmoother_ms": jac_or_gs_ms, "halo_exchange_ms": halo_ms, "partition_rank0": pinfo,
-        "fine_presmoother_gbs": (2 if args.smoother == "gs" else 1) * bytes_residual(nl, nnzl) / (jac_or_gs_ms * 1e-3) / 1e9,
+        "fine_presmoother_gbs": (2 * bytes_residual(nl, nnzl) if args.smoother == "gs" else bytes_residual(nl, nnzl, vb0)) / (jac_or_gs_ms * 1e-3) / 1e9,
         "phase_ms_per_level": {ph: [round(float(v), 4) for v in prof[:, i]] for i, ph in enumerate(phases)},
-        "levels": infos, "setup_s": t_setup, "upload_s": t_upload, "max_abs_err_vs_ones": err,
+        "levels": infos, "value_bytes_per_level": stor, "setup_s": t_setup, "upload_s": t_upload, "max_abs_err_vs_ones": err,
         "residual_history_first_last": [float(hist[0]), float(hist[-1])],
     }
     # ---- CPU baseline beside it: the oracle port on one host core, bounded sample -------------------------

@@ -217,6 +217,9 @@ int32_t b200amg_num_levels(b200amg_handle_t h);  /* length(ml) = levels + 1 */
 int32_t b200amg_level_info(b200amg_handle_t h, int32_t level, int64_t* n, int64_t* nnz_a,
                            int64_t* nnz_p, int64_t* wavefronts);
 /* kernels launched by this handle since creation (graph replays count their kernel nodes). */
+/* Bytes per stored matrix VALUE the bandwidth kernels read on a level (cap >= 3): out[0] A, out[1] P, out[2] R — 4 when the
+ * lossless binary32 copy is in use (B200AMG_OPT_FP32_STORAGE), 8 for fp64, 0 when the operator does not exist on this rank. */
+int32_t b200amg_storage_info(b200amg_handle_t h, int32_t level, int32_t* out, int32_t cap);
 int64_t b200amg_launch_count(b200amg_handle_t h);
 /* Communication counters of a row-partitioned handle (cap >= 4): [0] NCCL groups / collectives enqueued so far, [1] halo
  * exchanges done over peer memory so far, [2] 1 if halo exchanges use peer memory (CUDA IPC mappings of the neighbours'
@@ -249,11 +252,18 @@ int32_t b200amg_profile_cycle(b200amg_handle_t h, int32_t cycle, double* ms, int
  * thread-block cluster of <= 2^GS_DSM_MAX_CTAS_LOG2 CTAs (default 2: 4 CTAs, ~68 000 rows; up to 4: 16 CTAs, ~260 000 rows)
  * are swept by ONE cluster with x in distributed shared memory (csrc/device/dsm_gs.cuh); 0 = the GS_MODE kernels on every
  * level.  GS_DSM_FENCE bit 0 / bit 1 add a cluster-scope fence on the producer / consumer side of its hand-off.
+ * FP32_STORAGE (default: the environment variable B200AMG_FP32_STORAGE at upload time, 0 if unset): an operator all of whose
+ * values are exactly representable in binary32 (stencils, aggregation prolongators, any hierarchy built from Float32 input —
+ * test/runtests.jl:244-259) is ALSO stored with 4-byte values when B200AMG_FP32_STORAGE=1 is set while the hierarchy is
+ * uploaded, and the bandwidth kernels (SpMV, residual, restriction / prolongation, Jacobi) read that copy: 8 instead of 12
+ * bytes per entry, the same fp64 products and sums, bit-identical results; 0 = read the 8-byte values.  Off by default
+ * because it measured slower on B200.
  * Cycle graphs already captured keep the values they were captured with. */
 enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1, B200AMG_OPT_STREAM_CHUNK = 2, B200AMG_OPT_GS_MODE = 3, B200AMG_OPT_GS_ACQUIRE = 4, B200AMG_OPT_GS_POLL_SLEEP = 5,
        B200AMG_OPT_GS_GATE_SLEEP = 6, B200AMG_OPT_GS_CTA_ROWS = 7,
        B200AMG_OPT_GS_MAIL_MIN_WIDTH = 8, B200AMG_OPT_GS_CLUSTER = 9,
-       B200AMG_OPT_PART_LEVELS = 12, B200AMG_OPT_GS_DSM = 13, B200AMG_OPT_GS_DSM_FENCE = 14, B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2 = 15 };
+       B200AMG_OPT_PART_LEVELS = 12, B200AMG_OPT_GS_DSM = 13, B200AMG_OPT_GS_DSM_FENCE = 14, B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2 = 15,
+       B200AMG_OPT_FP32_STORAGE = 17 };
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
 int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
 /* Diagnostics: run one dataflow Gauss-Seidel sweep (forward / backward) of `level` on the level's

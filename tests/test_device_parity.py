@@ -387,6 +387,52 @@ def test_no_level_hierarchy_and_quirks(amg):
     assert x32.dtype == np.float64                                           # promote(eltype(A), eltype(b)) runtests.jl:244-259
 
 
+def test_precision_and_fp32_storage(amg, jac, monkeypatch):
+    """test/runtests.jl:244-259 ("Precision"): eltype(_solve(ml, b)) = promote(eltype(A), eltype(b)) for every Float32 / Float64
+    mix — and the device side of it: operators whose values are exactly representable in binary32 (a stencil; EVERY level of a
+    hierarchy built from a Float32 matrix) are read as 4-byte values by the bandwidth kernels, with bit-identical results."""
+    a = amg.poisson(100)
+    b = _rng(5).random(100)
+    for T, V in ((np.float64, np.float64), (np.float32, np.float32), (np.float64, np.float32), (np.float32, np.float64)):
+        ml = amg.smoothed_aggregation(a.astype(T))
+        x = amg._solve(ml, b.astype(V))
+        assert x.dtype == np.promote_types(T, V), (T, V, x.dtype)
+        ml.release()
+    # lossless narrow storage on a Float64 hierarchy: the stencil level qualifies, the Galerkin products do not
+    monkeypatch.setenv("B200AMG_FP32_STORAGE", "1")              # (read when a hierarchy is uploaded; off by default, DESIGN §4)
+    A = amg.poisson((40, 40, 40))
+    ml = amg.ruge_stuben(A, presmoother=jac, postsmoother=jac)
+    dev = ml.device()
+    assert dev.storage_info(0)["A"] == 4 and dev.storage_info(1)["A"] == 8
+    r = _rng(6)
+    x0, bb = r.standard_normal(A.n), r.standard_normal(A.n)
+    got = {}
+    for on in (1, 0):
+        dev.set_option(17, on)                                   # B200AMG_OPT_FP32_STORAGE
+        assert dev.storage_info(0)["A"] == (4 if on else 8)
+        y = dev.apply(0, 0, np.empty(A.n), x0)
+        res = dev.residual(0, np.empty(A.n), bb, x0)
+        xs, hist = amg._solve(ml, bb, log=True, maxiter=12)
+        got[on] = (y, res, xs, hist)
+    for u, v in zip(got[1], got[0]):
+        assert np.array_equal(u, v)                              # the same fp64 products and sums: identical bits
+    ml.release()
+    # a Float32 hierarchy: 4-byte values on every level, fp64 arithmetic; against the oracle on the same (Float32-valued) operators
+    A32 = amg.poisson((24, 24, 24)).astype(np.float32)
+    for build, kw in ((amg.ruge_stuben, dict(presmoother=jac, postsmoother=jac)), (amg.smoothed_aggregation, dict(presmoother=jac, postsmoother=jac)),
+                      (amg.ruge_stuben, {})):
+        ml = build(A32, **kw)
+        dev = ml.device()
+        assert all(dev.storage_info(i)["A"] == 4 and dev.storage_info(i)["P"] == 4 and dev.storage_info(i)["R"] == 4 for i in range(len(ml.levels)))
+        b32 = r.random(A32.n).astype(np.float32)
+        x, hist = amg._solve(ml, b32, log=True, reltol=1e-7)          # (the default tolerance is sqrt(eps(Float32)) here: multilevel.jl:160)
+        assert x.dtype == np.float32
+        xr, histr = oracle.OracleHierarchy(ml).solve(b32.astype(np.float64), log=True, reltol=1e-7)
+        assert len(hist) == len(histr) and np.allclose(hist, histr, rtol=TOL_HIST)
+        assert np.linalg.norm(x - xr) <= 1e-6 * np.linalg.norm(xr)          # x was rounded to Float32 at the boundary
+        ml.release()
+
+
 # ---- larger sizes: properties that need no oracle run -------------------------------------------
 def test_properties_at_size(amg, jac):
     A = amg.poisson((96, 96, 96))
