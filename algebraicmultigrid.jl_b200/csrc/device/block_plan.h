@@ -464,11 +464,12 @@ static inline BlockPlan build_block_plan(const HostCsr& w, const BlockPlanParams
 //   code = 0xC0000000             the diagonal
 // dpos[row] = position of the row's diagonal in the value array (-1: none).
 constexpr int kBlockCodeNear = (int)0x80000000u, kBlockCodeDiag = (int)0xC0000000u;
-static inline void build_block_codes(const BlockPlan& P, const HostCsr& wp, std::vector<int>& code_fwd, std::vector<int>& code_bwd,
-                                     std::vector<int>& dpos) {
-  code_fwd.assign(wp.idx.size(), 0);
-  code_bwd.assign(wp.idx.size(), 0);
-  dpos.assign((size_t)P.n, -1);
+static inline void build_block_codes(const BlockPlan& P, const HostCsr& wp, hvec<int>& code_fwd, hvec<int>& code_bwd, hvec<int>& dpos) {
+  code_fwd.resize(wp.idx.size());   // (no zero fill: the tiles cover every row, every entry is written below)
+  code_bwd.resize(wp.idx.size());
+  dpos.resize((size_t)P.n);
+#pragma omp parallel for schedule(static)
+  for (int64_t r = 0; r < P.n; ++r) dpos[(size_t)r] = -1;
   const int W = P.window, WE = P.window_eff;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int t = 0; t < P.ntiles; ++t) {

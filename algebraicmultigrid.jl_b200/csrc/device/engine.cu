@@ -213,8 +213,8 @@ static T* dev_alloc(int64_t count) {
   CUDA_OK(cudaMalloc(&p, sizeof(T) * (size_t)std::max<int64_t>(count, 1)));
   return p;
 }
-template <typename T>
-static T* dev_upload(const std::vector<T>& v, int64_t pad = 0) {
+template <typename T, typename Al>
+static T* dev_upload(const std::vector<T, Al>& v, int64_t pad = 0) {
   T* p = dev_alloc<T>((int64_t)v.size() + pad);
   if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
   return p;
@@ -606,7 +606,7 @@ struct SmootherMatrix {
         }
         if (!pass.ok) {
           UploadTimer t_codes("block entry codes");
-          std::vector<int> cf, cb, dp;
+          hvec<int> cf, cb, dp;
           build_block_codes(plan, symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA, cf, cb, dp);
           block.code_fwd = dev_upload(cf, 8);
           block.code_bwd = dev_upload(cb, 8);
@@ -647,7 +647,7 @@ struct SmootherMatrix {
       d_new_of_old = dev_upload(perm.new_of_old);
       d_old_of_new = dev_upload(perm.old_of_new);
     }
-    At.upload(*hAt);
+    { UploadTimer t("operator to device + tiles"); At.upload(*hAt); }
     if (symmetric_bits) A.alias(At);
     else if (need_true_A || symmetry == B200AMG_SYMMETRY_NONE) A.upload(*hA);
     const HostCsr& w = symmetry == B200AMG_SYMMETRY_HERMITIAN ? *hAt : *hA;
@@ -674,8 +674,9 @@ struct SmootherMatrix {
       fwd.n = bwd.n = n;
       return;
     }
-    if (need_fwd) fwd.upload(lvlptr, false, mean, walked().lanes);
-    if (need_bwd) bwd.upload(lvlptr, true, mean, walked().lanes);
+    { UploadTimer t("sweep schedules"); if (need_fwd) fwd.upload(lvlptr, false, mean, walked().lanes);
+    if (need_bwd) bwd.upload(lvlptr, true, mean, walked().lanes); }
+    UploadTimer t_plans("sweep tile plans (dsm / tile / mailboxes)");
     if ((need_fwd || need_bwd) && n > 0) {
       d_fwd_lvlptr = dev_upload(lvlptr, 8);
       nlev = (int)lvlptr.size() - 1;

@@ -4,6 +4,8 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <utility>
 #include <vector>
 
 namespace b200amg {
@@ -11,10 +13,26 @@ namespace b200amg {
 // ------------------------------------------------------------------------------------------
 // host-side sparse staging (int32, 0-based, "by rows" = compressed along the first index)
 // ------------------------------------------------------------------------------------------
+// The staging arrays of a 256^3 hierarchy are 0.5-1.3 GB each and every one of them is completely overwritten by a parallel
+// loop right after it is sized: std::vector's value-initialisation would first zero (and page-fault) them on ONE thread.
+// This allocator default-initialises instead, so the first touch happens in the parallel fill.
+template <class T>
+struct NoInitAlloc : std::allocator<T> {
+  template <class U> struct rebind { using other = NoInitAlloc<U>; };
+  NoInitAlloc() = default;
+  template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+  template <class U, class... Args>
+  void construct(U* p, Args&&... args) {
+    if constexpr (sizeof...(Args) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<Args>(args)...);
+  }
+};
+template <class T> using hvec = std::vector<T, NoInitAlloc<T>>;
+
 struct HostCsr {
   int64_t nrows = 0, ncols = 0;
-  std::vector<int> ptr, idx;
-  std::vector<double> val;
+  hvec<int> ptr, idx;      // (resize() leaves new elements uninitialised: every producer overwrites them all)
+  hvec<double> val;
   int64_t nnz() const { return ptr.empty() ? 0 : ptr.back(); }
 };
 
