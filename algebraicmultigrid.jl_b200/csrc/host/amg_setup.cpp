@@ -235,25 +235,28 @@ int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const
                              const idx_t* Tj, idx_t* splitting) {
   const int64_t n = n_;
   enum { F_NODE = 0, C_NODE = 1, U_NODE = 2 };
-  std::vector<int64_t> lambda(n + 1, 0), interval_ptr(n + 2, 0), interval_count(n + 2, 0);
-  std::vector<int64_t> index_to_node(n + 1, 0), node_to_index(n + 1, 0);
+  // (32-bit bookkeeping: the pass is sequential and latency-bound on five n-sized arrays hit at random; n < 2^31 - 2 is
+  // guaranteed by the int32 index type of the matrices)
+  using bk_t = int32_t;
+  std::vector<bk_t> lambda(n + 1, 0), interval_ptr(n + 2, 0), interval_count(n + 2, 0);
+  std::vector<bk_t> index_to_node(n + 1, 0), node_to_index(n + 1, 0);
   // 1-based: node i in 1..n ; arrays indexed 1..n(+1)
   for (int64_t i = 1; i <= n; ++i) {
-    lambda[i] = Sp[i] - Sp[i - 1];
+    lambda[i] = (bk_t)(Sp[i] - Sp[i - 1]);
     interval_count[lambda[i] + 1] += 1;
   }
   // accumulate!(+, interval_ptr[2:end], interval_count[1:end-1])
   {
     int64_t acc = 0;
-    for (int64_t k = 1; k <= n; ++k) { acc += interval_count[k]; interval_ptr[k + 1] = acc; }
+    for (int64_t k = 1; k <= n; ++k) { acc += interval_count[k]; interval_ptr[k + 1] = (bk_t)acc; }
   }
   std::fill(interval_count.begin(), interval_count.end(), 0);
   for (int64_t i = 1; i <= n; ++i) {
     const int64_t lambda_i = lambda[i] + 1;
     interval_count[lambda_i] += 1;
     const int64_t index = interval_ptr[lambda_i] + interval_count[lambda_i];
-    index_to_node[index] = i;
-    node_to_index[i] = index;
+    index_to_node[index] = (bk_t)i;
+    node_to_index[i] = (bk_t)index;
   }
   for (int64_t i = 1; i <= n; ++i) splitting[i - 1] = (lambda[i] == 0) ? F_NODE : U_NODE;
 
@@ -275,14 +278,14 @@ int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const
             const int64_t old_pos = node_to_index[rowk];
             const int64_t new_pos = interval_ptr[lambda_k] + interval_count[lambda_k];
             const int64_t swap_node = index_to_node[new_pos];
-            index_to_node[old_pos] = swap_node;
-            index_to_node[new_pos] = rowk;
-            node_to_index[rowk] = new_pos;
-            node_to_index[swap_node] = old_pos;
+            index_to_node[old_pos] = (bk_t)swap_node;
+            index_to_node[new_pos] = (bk_t)rowk;
+            node_to_index[rowk] = (bk_t)new_pos;
+            node_to_index[swap_node] = (bk_t)old_pos;
             lambda[rowk] += 1;
             interval_count[lambda_k] -= 1;
             interval_count[lambda_k + 1] += 1;
-            interval_ptr[lambda_k + 1] = new_pos - 1;
+            interval_ptr[lambda_k + 1] = (bk_t)(new_pos - 1);
           }
         }
       }
@@ -295,10 +298,10 @@ int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const
         const int64_t old_pos = node_to_index[row];
         const int64_t new_pos = interval_ptr[lambda_j] + 1;
         const int64_t swap_node = index_to_node[new_pos];
-        index_to_node[old_pos] = swap_node;
-        index_to_node[new_pos] = row;
-        node_to_index[row] = new_pos;
-        node_to_index[swap_node] = old_pos;
+        index_to_node[old_pos] = (bk_t)swap_node;
+        index_to_node[new_pos] = (bk_t)row;
+        node_to_index[row] = (bk_t)new_pos;
+        node_to_index[swap_node] = (bk_t)old_pos;
         lambda[row] -= 1;
         interval_count[lambda_j] -= 1;
         interval_count[lambda_j - 1] += 1;

@@ -507,6 +507,14 @@ def run_ours(args):
                         "launches_per_step": launches_per_step, "share_of_step": float(sm_ms[li]) / (ms / K),
                         "how_timed": "CUDA events around each phase of one cycle replayed eagerly (b200amg_profile_cycle), after the timed region",
                         "traffic": None}
+            if args.smoother == "gs" and args.size == 256 and args.dim == 3 and args.method == "rs" and li == 1:
+                try:           # static: one ncu --set full capture of this kernel on this level (not measured in this run)
+                    with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
+                        t = json.load(f)["gs_tile_kernel<4>@poisson256_level1_one_direction"]
+                    roofline["traffic"] = t["dram_bytes_read"] + t["dram_bytes_write"]
+                    roofline["traffic_source"] = "static: profiles/r02_ncu_traffic.json (one `ncu --set full` capture of gs_tile_kernel<4> on level 1 of this workload)"
+                except Exception:
+                    pass
     roofline["whole_step"] = whole_step
     roofline["fine_level_residual_spmv"] = spmv_roofline
     pinfo = dev.partition_info() if world > 1 else None
