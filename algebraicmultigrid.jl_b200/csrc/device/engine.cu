@@ -2897,9 +2897,64 @@ int32_t b200amg_pcg(b200amg_handle_t h, double* x, const double* b, int32_t cycl
                     double reltol, double* residuals, int32_t cap, int32_t* nres, int32_t* iters, int32_t memkind) {
   API_BEGIN
   check_ready(h);
-  check_not_partitioned(h, "pcg");
   REQUIRE(x && b, B200AMG_ERR_BAD_ARG, "null vector");
   REQUIRE(cycle >= 0 && cycle <= 2, B200AMG_ERR_BAD_ARG, "unknown cycle %d", cycle);
+  if (h->part) {
+    // Row-partitioned handle: every rank holds its row block of x, r, u, q; z = Pl \ r is the partitioned cycle; q = A u needs u's
+    // halo (u travels in the level's exported `res` vector); dots = local partial sums + one all-reduce of a double (the same
+    // bits on every rank, so every rank takes the same loop decisions).  Same recurrences as the single-GPU loop below.
+    Part& P = *h->part;
+    const int64_t nl = P.plan.nloc, nalloc = std::max<int64_t>(nl, 1);
+    if (!h->pcg_u) { h->pcg_u = dev_alloc<double>(nalloc); h->pcg_q = dev_alloc<double>(nalloc); h->pcg_x = dev_alloc<double>(nalloc); }
+    double* S = h->scalars;
+    auto dot_part = [&](const double* u, const double* v, double* out) {
+      dot_partial_kernel<<<kRedBlocks, kThreads, 0, h->stream>>>(nl, u, v, h->partial);
+      count_launch(h);
+      reduce_final_kernel<<<1, kThreads, 0, h->stream>>>(kRedBlocks, h->partial, out, 0);
+      count_launch(h);
+      allreduce_scalar(h, out);
+    };
+    part_load(h, P.b, b, memkind);                                                         // r = b (x starts at zero)
+    CUDA_OK(cudaMemsetAsync(h->pcg_x, 0, sizeof(double) * (size_t)nalloc, h->stream));
+    CUDA_OK(cudaMemsetAsync(h->pcg_u, 0, sizeof(double) * (size_t)nalloc, h->stream));
+    set_scalar_kernel<<<1, 32, 0, h->stream>>>(S + 1, 1.0);
+    count_launch(h);
+    dot_part(P.b, P.b, S);
+    double residual = std::sqrt(read_scalar(h, S));
+    const double tol = std::max(reltol * residual, abstol);
+    int nr = 0, it = 0;
+    if (residuals && nr < cap) residuals[nr++] = residual;
+    const unsigned g = grid_for(nalloc);
+    while (!(it >= maxiter || residual <= tol)) {
+      CUDA_OK(cudaMemsetAsync(P.x, 0, sizeof(double) * (size_t)nalloc, h->stream));         // ldiv!: x .= 0
+      run_cycle(h, cycle);                                                                 // c = Pl \ r   (c == P.x, r == P.b)
+      copy_scalar_kernel<<<1, 32, 0, h->stream>>>(S + 2, S + 1);
+      count_launch(h);
+      dot_part(P.x, P.b, S + 1);                                                           // rho = c.r
+      if (nl > 0) {
+        pcg_update_u_kernel<<<g, kThreads, 0, h->stream>>>(nl, P.x, h->pcg_u, S + 1, S + 2);
+        count_launch(h);
+        CUDA_OK(cudaMemcpyAsync(P.res, h->pcg_u, sizeof(double) * (size_t)nl, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      halo_exchange(h, P, P.res);
+      spmv(h, P.A, P.res, h->pcg_q);                                                       // q = A u
+      halo_consumed(h);
+      dot_part(h->pcg_u, h->pcg_q, S + 3);                                                 // u.q
+      if (nl > 0) {
+        pcg_update_xr_kernel<<<g, kThreads, 0, h->stream>>>(nl, h->pcg_x, P.b, h->pcg_u, h->pcg_q, S + 1, S + 3);
+        count_launch(h);
+      }
+      dot_part(P.b, P.b, S);
+      residual = std::sqrt(read_scalar(h, S));
+      if (residuals && nr < cap) residuals[nr++] = residual;
+      ++it;
+    }
+    part_store(h, x, h->pcg_x, memkind);
+    sync_and_check(h);
+    if (nres) *nres = nr;
+    if (iters) *iters = it;
+    return B200AMG_OK;
+  }
   const int64_t n = h->n0;
   const DevCsr& A = h->levels.empty() ? h->finalA : h->levels[0]->M.A;
   if (!h->pcg_u) { h->pcg_u = dev_alloc<double>(n); h->pcg_q = dev_alloc<double>(n); h->pcg_x = dev_alloc<double>(n); }

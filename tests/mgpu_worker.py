@@ -56,6 +56,21 @@ def main():
                     failures.append((method, dims, plevels, cname))
             elif not same:
                 failures.append(("rank", rank))
+        # device-resident CG preconditioned by the PARTITIONED V-cycle (b200amg_pcg on a row-partitioned handle) against the oracle's
+        xc, info = amg.cg(A, b, Pl=amg.aspreconditioner(ml), reltol=1e-10, log=True)
+        tc = torch.from_numpy(xc.copy()).cuda()
+        dist.broadcast(tc, src=0)
+        same = bool(np.array_equal(tc.cpu().numpy(), xc))
+        if rank == 0:
+            xcr = H.pcg(b, reltol=1e-10)
+            ec = np.linalg.norm(xc - xcr) / np.linalg.norm(xcr)
+            okc = info["iters"] == H.iters and ec < 1e-8 and same
+            print(f"[mgpu] {method} {dims} part_levels={plevels} pcg: iters {info['iters']}/{H.iters} x {ec:.1e} same_on_all_ranks={same} {'OK' if okc else 'FAIL'}",
+                  flush=True)
+            if not okc:
+                failures.append((method, dims, plevels, "pcg"))
+        elif not same:
+            failures.append(("rank", rank, "pcg"))
         if rank == 0:
             print("[mgpu] partition:", ml.device().partition_info(), flush=True)
         ml.release()
