@@ -296,7 +296,7 @@ def other_configs(amg, torch, local):
         out["C5"] = {"error": str(exc)[:300]}
     try:                                   # ---- synthetic 3-D elasticity (north_star: "synthetic Poisson / elasticity matrices")
         t0 = time.time()
-        A, bvec, B = amg.elasticity_3d(40, 40, 40)
+        A, bvec, B = amg.elasticity_3d(48, 48, 48)
         t_gen = time.time() - t0
         res = {}
         for name, kw in (("gauss_seidel", {}), ("jacobi_0.5", {"presmoother": amg.Jacobi(0.5), "postsmoother": amg.Jacobi(0.5)})):
@@ -319,7 +319,7 @@ def other_configs(amg, torch, local):
                          "relative_residual": float(np.linalg.norm(A.matvec(xh) - bvec) / np.linalg.norm(bvec)),
                          "fine_spmv_gbs_l2_flushed": bytes_spmv(A.n, A.nnz, dev.storage_info(0)["A"] or 8) / (dev.time_kernel(0, 0, reps=10, flush_l2=True) * 1e-3) / 1e9}
             ml.release()
-        out["elasticity_3d"] = {"workload": "elasticity_3d(40,40,40): Q1 hexahedra, 3 dofs per node, clamped face, smoothed_aggregation with the six "
+        out["elasticity_3d"] = {"workload": "elasticity_3d(48,48,48): Q1 hexahedra, 3 dofs per node, clamped face, smoothed_aggregation with the six "
                                             "rigid-body modes as near-null-space, device-resident CG preconditioned by one V-cycle, reltol 1e-8",
                                 "n": A.n, "nnz": A.nnz, "generate_s": t_gen, "smoothers": res}
     except Exception as exc:
