@@ -578,7 +578,10 @@ struct SmootherMatrix {
     // rows) 0.19 / 0.088 vs 0.22 / 0.093; on the irregular coarse levels in between (19-124 entries per row) the blocked
     // sweep's per-stage pipeline latency loses (10.3 / 8.7 / 7.2 / 9.0 / 2.6 vs 7.8 / 6.3 / 5.0 / 6.2 / 2.2).
     // B200AMG_GS_BLOCK: 0 never, 1 (default) by that rule, 2 always.
-    const int block_mode = env_int("B200AMG_GS_BLOCK", 1);
+    // B200AMG_GS_MULTICOLOR=1 (NOT parity: the sweep relaxes colour after colour instead of in index order): wavefront kernels
+    // on a greedy colouring, see greedy_colours().
+    const bool multicolor = env_int("B200AMG_GS_MULTICOLOR", 0) != 0;
+    const int block_mode = multicolor ? 0 : env_int("B200AMG_GS_BLOCK", 1);
     const double mean_row = n ? (double)hAt_in.nnz() / (double)n : 0.0;
     const bool block_wanted = block_mode >= 2 || (block_mode == 1 && (mean_row <= 8.0 || n <= 1024));
     if ((need_fwd || need_bwd) && n > 0 && pattern_symmetric && block_wanted) {
@@ -628,7 +631,7 @@ struct SmootherMatrix {
       const HostCsr& wt0 = symmetric_bits ? w0 : (symmetry == B200AMG_SYMMETRY_HERMITIAN ? hA_in : hAt_in);
       int nlev = 0;
       std::vector<int> level;
-      { UploadTimer t("wavefront levels"); level = wavefront_levels(w0, wt0, &nlev); }
+      { UploadTimer t("wavefront levels"); level = multicolor ? greedy_colours(w0, wt0, &nlev) : wavefront_levels(w0, wt0, &nlev); }
       UploadTimer t_perm("renumbering + permute");
       lvlptr.assign(nlev + 1, 0);
       for (int64_t i = 0; i < n; ++i) lvlptr[level[i] + 1]++;

@@ -125,6 +125,33 @@ static inline std::vector<int> wavefront_levels(const HostCsr& a, const HostCsr&
   return level;
 }
 
+// MULTICOLOUR ordering (NOT the reference's: an explicit opt-in, B200AMG_GS_MULTICOLOR=1): greedy colouring of the symmetrised
+// pattern in index order (smallest colour no neighbour holds).  Used in place of the wavefront number, it makes the sweep
+// relax colour after colour — a Gauss-Seidel sweep in a DIFFERENT row order (a handful of wide, independent "wavefronts":
+// bandwidth-bound) whose iterates differ from gs! (src/smoother.jl:73-90) while the fixed point is the same.
+static inline std::vector<int> greedy_colours(const HostCsr& a, const HostCsr& at, int* ncol_out) {
+  const int64_t n = a.nrows;
+  std::vector<int> colour((size_t)n, -1);
+  std::vector<int64_t> seen;   // seen[c] == i: colour c is taken by a neighbour of row i
+  int ncol = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    auto mark = [&](const HostCsr& m) {
+      for (int k = m.ptr[i]; k < m.ptr[i + 1]; ++k) {
+        const int j = m.idx[k];
+        if (j != i && colour[(size_t)j] >= 0) seen[(size_t)colour[(size_t)j]] = i;
+      }
+    };
+    mark(a);
+    if (&at != &a) mark(at);
+    int c = 0;
+    while (c < ncol && seen[(size_t)c] == i) ++c;
+    if (c == ncol) { ++ncol; seen.push_back(-1); }
+    colour[(size_t)i] = c;
+  }
+  *ncol_out = ncol;
+  return colour;
+}
+
 // A renumbering of one level: new index p holds old row old_of_new[p]; empty vectors = identity.
 struct HostPerm {
   std::vector<int> new_of_old, old_of_new;

@@ -294,6 +294,34 @@ def other_configs(amg, torch, local):
         ml.release()
     except Exception as exc:
         out["C5"] = {"error": str(exc)[:300]}
+    try:                                   # ---- the headline workload with MULTICOLOUR Gauss-Seidel: NOT parity, the bandwidth-bound ceiling
+        os.environ["B200AMG_GS_MULTICOLOR"] = "1"
+        try:
+            A = amg.poisson((256, 256, 256))
+            t0 = time.time()
+            ml = amg.ruge_stuben(A)
+            t_setup = time.time() - t0
+            dev = ml.device()
+        finally:
+            os.environ.pop("B200AMG_GS_MULTICOLOR", None)
+        b = torch.from_numpy(A.matvec(np.ones(A.n))).to(dev_t)
+        x = torch.zeros(A.n, dtype=torch.float64, device=dev_t)
+        dev.solve(x, b, 0, 3, 0.0, 0.0, True)
+        x.zero_()
+        its = 20
+        ms_it = time_solve(dev, x, b, its, cold=False)
+        x.zero_()
+        hist, _ = dev.solve(x, b, 0, its, 0.0, 0.0, True)
+        out["C3_multicolour_gauss_seidel"] = {
+            "workload": "poisson((256x256x256)) fp64, ruge_stuben V-cycle, pre/post symmetric Gauss-Seidel relaxed COLOUR BY COLOUR (greedy colouring; "
+                        "B200AMG_GS_MULTICOLOR=1) instead of in index order",
+            "parity": "NONE - a different row order than gs! (src/smoother.jl:73-90): same fixed point, different iterates; shown as the "
+                      "bandwidth-bound ceiling next to the exact-order headline (SURVEY 7.2-A)",
+            "iters_per_s": 1e3 / ms_it, "ms_per_iter": ms_it, "wavefronts_per_level": [dev.level_info(i)["wavefronts"] for i in range(dev.nlevels)],
+            "residual_history_first_last": [float(hist[0]), float(hist[-1])], "max_abs_err_vs_ones": float((x - 1.0).abs().max().item())}
+        ml.release()
+    except Exception as exc:
+        out["C3_multicolour_gauss_seidel"] = {"error": str(exc)[:300]}
     try:                                   # ---- synthetic 3-D elasticity (north_star: "synthetic Poisson / elasticity matrices")
         t0 = time.time()
         A, bvec, B = amg.elasticity_3d(48, 48, 48)

@@ -433,6 +433,42 @@ def test_precision_and_fp32_storage(amg, jac, monkeypatch):
         ml.release()
 
 
+def test_multicolour_gauss_seidel_is_an_explicit_non_parity_mode(amg, monkeypatch):
+    """B200AMG_GS_MULTICOLOR=1 ("offer multicolor as an explicitly non-parity fast mode"): the sweep relaxes colour
+    after colour of a greedy colouring instead of in index order.  On the 7-point stencil the colouring is red-black, so one
+    forward sweep must equal red-black Gauss-Seidel computed directly; as a smoother it converges to the same solution in a
+    comparable number of iterations, but its iterates are NOT the reference's."""
+    monkeypatch.setenv("B200AMG_GS_MULTICOLOR", "1")
+    dims = (14, 12, 10)
+    A = amg.poisson(dims)
+    S = A.to_scipy().tocsr()
+    r = _rng(21)
+    x0, b = r.standard_normal(A.n), r.standard_normal(A.n)
+    x = x0.copy()
+    amg.GaussSeidel(amg.ForwardSweep())(A, x, b, amg.HermitianSymmetry())
+    i, j, k = np.meshgrid(np.arange(dims[0]), np.arange(dims[1]), np.arange(dims[2]), indexing="ij")
+    colour = ((i + j + k) % 2).ravel(order="F")                     # first index fastest (gallery.jl:42-63)
+    d = S.diagonal()
+    ref = x0.copy()
+    for c in (0, 1):
+        rows = np.nonzero(colour == c)[0]
+        ref[rows] = (b[rows] - (S[rows] @ ref - d[rows] * ref[rows])) / d[rows]
+    assert relinf(x, ref) <= 1e-13
+    parity = oracle.smooth(A, amg.GaussSeidel(amg.ForwardSweep()), x0.copy(), b)
+    assert relinf(x, parity) > 1e-3                                  # a different ordering: not the reference's iterates
+    A = amg.poisson((28, 28, 28))
+    bb = A.matvec(np.ones(A.n))
+    ml = amg.ruge_stuben(A)
+    xs, hist = amg._solve(ml, bb, log=True)
+    assert hist[-1] <= 1.5e-8 * hist[0] and np.abs(xs - 1.0).max() <= 1e-6
+    monkeypatch.delenv("B200AMG_GS_MULTICOLOR")
+    mlp = amg.ruge_stuben(A)
+    _, histp = amg._solve(mlp, bb, log=True)
+    assert len(histp) <= len(hist) <= 2 * len(histp)                 # a somewhat weaker smoother than the lexicographic sweep (11 vs 7 entries here)
+    ml.release()
+    mlp.release()
+
+
 # ---- larger sizes: properties that need no oracle run -------------------------------------------
 def test_properties_at_size(amg, jac):
     A = amg.poisson((96, 96, 96))
