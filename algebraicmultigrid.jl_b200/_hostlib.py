@@ -55,6 +55,8 @@ def _declare(L):
     L.amgsetup_symmetric_strength.argtypes = [i64, i32p, i32p, f64p, C.c_double, i32p, i32p, f64p]
     L.amgsetup_remove_diag.restype = i64
     L.amgsetup_remove_diag.argtypes = [i64, i32p, i32p, f64p]
+    L.amgsetup_remove_diag_copy.restype = i64
+    L.amgsetup_remove_diag_copy.argtypes = [i64, i32p, i32p, C.c_void_p, i32p, i32p, C.c_void_p]
     L.amgsetup_rs_cf_splitting.restype = C.c_int
     L.amgsetup_rs_cf_splitting.argtypes = [i64, i32p, i32p, i32p, i32p, i32p]
     L.amgsetup_direct_interpolation.restype = i64
@@ -121,7 +123,7 @@ def classical_strength(at, theta):
     tr = np.empty(at.nnz, np.int32)
     tv = np.empty(at.nnz, np.float64)
     nnz = lib().amgsetup_classical_strength(at.n, at.colptr, at.rowval, at.nzval, float(theta), tp, tr, tv)
-    return _csc(at.m, at.n, tp, tr[:nnz].copy(), tv[:nnz].copy())
+    return _csc(at.m, at.n, tp, tr[:nnz], tv[:nnz])   # views: no copy (the untouched tail is never resident)
 
 
 def symmetric_strength(a, theta):
@@ -129,22 +131,37 @@ def symmetric_strength(a, theta):
     sr = np.empty(a.nnz, np.int32)
     sv = np.empty(a.nnz, np.float64)
     nnz = lib().amgsetup_symmetric_strength(a.n, a.colptr, a.rowval, a.nzval, float(theta), sp_, sr, sv)
-    return _csc(a.m, a.n, sp_, sr[:nnz].copy(), sv[:nnz].copy())
+    return _csc(a.m, a.n, sp_, sr[:nnz], sv[:nnz])
 
 
 def remove_diag(s):
-    """In place, like ``remove_diag!`` (the reference mutates the caller's S)."""
-    colptr, rowval, nzval = s.colptr, s.rowval, s.nzval
-    nnz = lib().amgsetup_remove_diag(s.n, colptr, rowval, nzval)
-    s.rowval = rowval[:nnz]
-    s.nzval = nzval[:nnz]
+    """``remove_diag!`` (``splitting.jl:8-18``): the caller's S is mutated like in the reference (its arrays are replaced by
+    the filtered ones, built on all cores)."""
+    cp = np.empty(s.n + 1, np.int32)
+    rv = np.empty(s.nnz, np.int32)
+    nz = np.empty(s.nnz, np.float64)
+    nnz = lib().amgsetup_remove_diag_copy(s.n, s.colptr, s.rowval, s.nzval.ctypes.data, cp, rv, nz.ctypes.data)
+    s.colptr = cp
+    s.rowval = rv[:nnz]
+    s.nzval = nz[:nnz]
     s._bitsym = None
     return s
 
 
+def offdiag_pattern(t):
+    """``(colptr, rowval)`` of ``t`` without its diagonal and without stored zeros: the pattern of
+    ``transpose(remove_diag!(transpose(t)))`` without forming either transpose."""
+    cp = np.empty(t.n + 1, np.int32)
+    rv = np.empty(t.nnz, np.int32)
+    nnz = lib().amgsetup_remove_diag_copy(t.n, t.colptr, t.rowval, t.nzval.ctypes.data, cp, rv, None)
+    return cp, rv[:nnz]
+
+
 def rs_cf_splitting(s, t):
+    """``t``: the transpose of ``s`` as a matrix or as a ``(colptr, rowval)`` pattern (only patterns are read)."""
     out = np.empty(s.n, np.int32)
-    rc = lib().amgsetup_rs_cf_splitting(s.n, s.colptr, s.rowval, t.colptr, t.rowval, out)
+    tcp, trv = (t.colptr, t.rowval) if hasattr(t, "colptr") else t
+    rc = lib().amgsetup_rs_cf_splitting(s.n, s.colptr, s.rowval, tcp, trv, out)
     if rc:
         raise RuntimeError(f"rs_cf_splitting failed ({rc})")
     return out

@@ -877,6 +877,12 @@ struct b200amg_hierarchy {
   DevCsr finalA;
   double* coarse_inv = nullptr;
   double* res_final = nullptr;
+  // coarse solver as a host callable (b200amg_set_coarse_callback): pinned staging vectors, the callable, its last status
+  b200amg_coarse_fn coarse_fn = nullptr;
+  void* coarse_user = nullptr;
+  double *coarse_hb = nullptr, *coarse_hx = nullptr;
+  volatile int32_t coarse_fn_status = 0;
+  int64_t coarse_fn_calls = 0;
   // level-0 work vectors
   int64_t n0 = 0;
   double *x0 = nullptr, *b0 = nullptr;
@@ -1525,8 +1531,24 @@ static double read_scalar(H* h, const double* dev) {
   return h->h_scalars[0];
 }
 
+// the host-callable coarse solver, run by the CUDA runtime between the two copies of coarse_solve (stream order; also
+// inside a captured cycle graph, as a host node).  No CUDA calls in here.
+static void CUDART_CB coarse_host_trampoline(void* p) {
+  H* h = static_cast<H*>(p);
+  const int32_t rc = h->coarse_fn(h->coarse_user, h->nfinal, 1, h->coarse_hx, h->coarse_hb);
+  ++h->coarse_fn_calls;
+  if (rc != 0 && h->coarse_fn_status == 0) h->coarse_fn_status = rc;
+}
+
 static void coarse_solve(H* h, double* x, const double* b) {
   if (h->nfinal == 0) return;
+  if (h->coarse_fn) {   // cs(x, b) on the host: src/multilevel.jl:180,228 with a callable from src/coarse_solver.jl:24-58
+    const size_t bytes = sizeof(double) * (size_t)h->nfinal;
+    CUDA_OK(cudaMemcpyAsync(h->coarse_hb, b, bytes, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaLaunchHostFunc(h->stream, coarse_host_trampoline, h));
+    CUDA_OK(cudaMemcpyAsync(x, h->coarse_hx, bytes, cudaMemcpyHostToDevice, h->stream));
+    return;
+  }
   dense_gemv_kernel<<<grid_for(h->nfinal), kThreads, 0, h->stream>>>((int)h->nfinal, h->coarse_inv, b, x);
   count_launch(h);
 }
@@ -1958,8 +1980,18 @@ static void part_store(H* h, double* dst_full, const double* src_local, int memk
 // ------------------------------------------------------------------------------------------
 static void set_device(H* h) { CUDA_OK(cudaSetDevice(h->device)); }
 // stream-synchronise and report a sweep kernel whose watchdog fired (a hand-off that never came: the result is not valid)
+static void check_coarse_callback(H* h) {
+  if (h->coarse_fn_status != 0) {
+    const int32_t rc = h->coarse_fn_status;
+    h->coarse_fn_status = 0;
+    char msg[128];
+    std::snprintf(msg, sizeof msg, "the coarse-solver callback returned %d: result discarded", (int)rc);
+    throw AmgError{B200AMG_ERR_CALLBACK, msg};
+  }
+}
 static void sync_and_check(H* h) {
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  check_coarse_callback(h);
   if (!h->gs_fault) return;
   int f = 0;
   CUDA_OK(cudaMemcpy(&f, h->gs_fault, sizeof(int), cudaMemcpyDeviceToHost));
@@ -2262,14 +2294,14 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
   API_END
 }
 
-int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n, const double* inv) {
-  API_BEGIN
+static void set_coarse_impl(H* h, const b200amg_csc_t* final_A, int64_t n, const double* inv, b200amg_coarse_fn fn, void* user) {
   REQUIRE(h && final_A, B200AMG_ERR_BAD_ARG, "null argument");
   REQUIRE(!h->finalized, B200AMG_ERR_STATE, "hierarchy already finalized");
   REQUIRE(final_A->m == n && final_A->n == n, B200AMG_ERR_DIM_MISMATCH, "final_A is %lld x %lld, coarse operator is %lld",
           (long long)final_A->m, (long long)final_A->n, (long long)n);
-  REQUIRE(n == 0 || inv, B200AMG_ERR_BAD_ARG, "null coarse operator");
-  REQUIRE(n <= 16384, B200AMG_ERR_UNSUPPORTED, "dense coarse operator limited to 16384 rows (got %lld)", (long long)n);
+  REQUIRE(n == 0 || inv || fn, B200AMG_ERR_BAD_ARG, "null coarse operator");
+  REQUIRE(fn || n <= 16384, B200AMG_ERR_UNSUPPORTED,
+          "dense coarse operator limited to 16384 rows (got %lld): use b200amg_set_coarse_callback for a larger coarsest level", (long long)n);
   if (!h->levels.empty())
     REQUIRE(h->levels.back()->nc == n, B200AMG_ERR_DIM_MISMATCH, "coarsest matrix has %lld rows, last level coarsens to %lld",
             (long long)n, (long long)h->levels.back()->nc);
@@ -2281,11 +2313,30 @@ int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int
   if (h->world == 1 || h->rank == 0) {
     HostCsr hAt = stage_csc_as_rows_of_transpose(final_A);
     h->finalA.upload(transpose(hAt));
-    std::vector<double> m(inv, inv + n * n);
-    h->coarse_inv = dev_upload(m);
+    if (fn) {
+      h->coarse_fn = fn;
+      h->coarse_user = user;
+      CUDA_OK(cudaMallocHost(&h->coarse_hb, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+      CUDA_OK(cudaMallocHost(&h->coarse_hx, sizeof(double) * (size_t)std::max<int64_t>(n, 1)));
+    } else {
+      std::vector<double> m(inv, inv + n * n);
+      h->coarse_inv = dev_upload(m);
+    }
     h->res_final = dev_alloc<double>(n);
   }
   h->have_coarse = true;
+}
+
+int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n, const double* inv) {
+  API_BEGIN
+  set_coarse_impl(h, final_A, n, inv, nullptr, nullptr);
+  API_END
+}
+
+int32_t b200amg_set_coarse_callback(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n, b200amg_coarse_fn fn, void* user) {
+  API_BEGIN
+  REQUIRE(fn, B200AMG_ERR_BAD_ARG, "null coarse-solver callback");
+  set_coarse_impl(h, final_A, n, nullptr, fn, user);
   API_END
 }
 
@@ -2622,6 +2673,7 @@ int32_t b200amg_destroy(b200amg_handle_t h) {
   h->finalA.release();
   cudaFree(h->coarse_inv); cudaFree(h->res_final); cudaFree(h->x0); cudaFree(h->b0);
   cudaFree(h->partial); cudaFree(h->scalars); cudaFree(h->gs_fault); cudaFreeHost(h->h_scalars);
+  cudaFreeHost(h->coarse_hb); cudaFreeHost(h->coarse_hx);
   cudaFree(h->pcg_u); cudaFree(h->pcg_q); cudaFree(h->pcg_x); cudaFree(h->flush); cudaFree(h->io_tmp);
   for (cudaEvent_t e : h->res_events) cudaEventDestroy(e);
   for (int c = 0; c < 3; ++c)
@@ -2873,7 +2925,7 @@ int32_t b200amg_coarse_solve(b200amg_handle_t h, double* x, const double* b, int
   to_dev(h, sb.p, b, h->nfinal, memkind);
   coarse_solve(h, sx.p, sb.p);
   from_dev(h, x, sx.p, h->nfinal, memkind);
-  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
   API_END
 }
 

@@ -15,8 +15,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <limits>
 #include <numeric>
 #include <vector>
@@ -25,6 +27,14 @@
 #endif
 
 typedef int32_t idx_t;
+
+static inline double wall_s() {
+#ifdef _OPENMP
+  return omp_get_wtime();
+#else
+  return (double)std::clock() / CLOCKS_PER_SEC;
+#endif
+}
 
 extern "C" {
 
@@ -225,6 +235,31 @@ int64_t amgsetup_remove_diag(int64_t n, idx_t* colptr, idx_t* rowval, double* nz
   return q;
 }
 
+// The same filter out of place and on all cores (count, prefix sum, fill): out_colptr[n+1], out_rowval / out_nzval sized
+// nnz(in).  out_nzval may be null (pattern only: what the C/F splitting reads).  Returns the new nnz.
+int64_t amgsetup_remove_diag_copy(int64_t n, const idx_t* colptr, const idx_t* rowval, const double* nzval,
+                                  idx_t* out_colptr, idx_t* out_rowval, double* out_nzval) {
+  out_colptr[0] = 0;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    idx_t kept = 0;
+    for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j) kept += (rowval[j] != i && nzval[j] != 0.0);
+    out_colptr[i + 1] = kept;
+  }
+  for (int64_t i = 0; i < n; ++i) out_colptr[i + 1] += out_colptr[i];
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    idx_t q = out_colptr[i];
+    for (idx_t j = colptr[i]; j < colptr[i + 1]; ++j)
+      if (rowval[j] != i && nzval[j] != 0.0) {
+        out_rowval[q] = rowval[j];
+        if (out_nzval) out_nzval[q] = nzval[j];
+        ++q;
+      }
+  }
+  return out_colptr[n];
+}
+
 // ---------------------------------------------------------------------------------------
 // Ruge-Stuben first-pass C/F splitting.  src/splitting.jl:25-159.
 // S: strength with diagonal removed; T = transpose(S).  Only the patterns are used.
@@ -234,16 +269,21 @@ int64_t amgsetup_remove_diag(int64_t n, idx_t* colptr, idx_t* rowval, double* nz
 int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const idx_t* Tp,
                              const idx_t* Tj, idx_t* splitting) {
   const int64_t n = n_;
-  enum { F_NODE = 0, C_NODE = 1, U_NODE = 2 };
-  // (32-bit bookkeeping: the pass is sequential and latency-bound on five n-sized arrays hit at random; n < 2^31 - 2 is
-  // guaranteed by the int32 index type of the matrices)
+  enum : uint8_t { F_NODE = 0, C_NODE = 1, U_NODE = 2 };
+  // The pass is sequential and bound by random accesses to n-sized arrays, so the bookkeeping is kept small: 32-bit
+  // (n < 2^31 - 2 is guaranteed by the int32 index type of the matrices), lambda and the bucket position of a node side by
+  // side in one 8-byte record (one cache line touched per node instead of two), and the C / F / U state in a byte array
+  // (the innermost test "is this neighbour still undecided" then runs mostly out of cache) that is widened into
+  // `splitting` at the end.  Statement order and index arithmetic (1-based) are the reference's.
   using bk_t = int32_t;
-  std::vector<bk_t> lambda(n + 1, 0), interval_ptr(n + 2, 0), interval_count(n + 2, 0);
-  std::vector<bk_t> index_to_node(n + 1, 0), node_to_index(n + 1, 0);
+  struct NodeRec { bk_t lambda, pos; };
+  std::vector<NodeRec> node(n + 1, NodeRec{0, 0});
+  std::vector<bk_t> interval_ptr(n + 2, 0), interval_count(n + 2, 0), index_to_node(n + 1, 0);
+  std::vector<uint8_t> state(n + 1, U_NODE);
   // 1-based: node i in 1..n ; arrays indexed 1..n(+1)
   for (int64_t i = 1; i <= n; ++i) {
-    lambda[i] = (bk_t)(Sp[i] - Sp[i - 1]);
-    interval_count[lambda[i] + 1] += 1;
+    node[i].lambda = (bk_t)(Sp[i] - Sp[i - 1]);
+    interval_count[node[i].lambda + 1] += 1;
   }
   // accumulate!(+, interval_ptr[2:end], interval_count[1:end-1])
   {
@@ -252,37 +292,78 @@ int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const
   }
   std::fill(interval_count.begin(), interval_count.end(), 0);
   for (int64_t i = 1; i <= n; ++i) {
-    const int64_t lambda_i = lambda[i] + 1;
+    const int64_t lambda_i = node[i].lambda + 1;
     interval_count[lambda_i] += 1;
     const int64_t index = interval_ptr[lambda_i] + interval_count[lambda_i];
     index_to_node[index] = (bk_t)i;
-    node_to_index[i] = (bk_t)index;
+    node[i].pos = (bk_t)index;
   }
-  for (int64_t i = 1; i <= n; ++i) splitting[i - 1] = (lambda[i] == 0) ? F_NODE : U_NODE;
+  for (int64_t i = 1; i <= n; ++i) state[i] = (node[i].lambda == 0) ? F_NODE : U_NODE;
 
+  // Software prefetch along the bucket order (hints only: a node met at distance D may still be moved before its turn, which
+  // costs nothing but the wasted line): records of the node 12 steps ahead, its neighbour lists 8 ahead, and for a node
+  // that is still undecided 4 steps ahead the records of the neighbours it would turn into F points.
   for (int64_t top_index = n; top_index >= 1; --top_index) {
+    if (top_index > 12) {
+      const int64_t i2 = index_to_node[top_index - 12];
+      __builtin_prefetch(&node[i2]);
+      __builtin_prefetch(&state[i2]);
+      __builtin_prefetch(&Sp[i2 - 1]);
+      __builtin_prefetch(&Tp[i2 - 1]);
+      const int64_t i3 = index_to_node[top_index - 8];
+      if (state[i3] != F_NODE) {
+        __builtin_prefetch(&Sj[Sp[i3 - 1]]);
+        __builtin_prefetch(&Tj[Tp[i3 - 1]]);
+      }
+      const int64_t i4 = index_to_node[top_index - 4];
+      if (state[i4] != F_NODE) {
+        for (idx_t j = Sp[i4 - 1]; j < Sp[i4]; ++j) {
+          const int64_t row = (int64_t)Sj[j] + 1;
+          __builtin_prefetch(&state[row]);
+          __builtin_prefetch(&Tp[row - 1]);
+        }
+        for (idx_t j = Tp[i4 - 1]; j < Tp[i4]; ++j) __builtin_prefetch(&node[(int64_t)Tj[j] + 1]);
+      }
+      const int64_t i5 = index_to_node[top_index - 2];
+      if (state[i5] != F_NODE) {
+        for (idx_t j = Sp[i5 - 1]; j < Sp[i5]; ++j) {
+          const int64_t row = (int64_t)Sj[j] + 1;
+          if (state[row] == U_NODE)
+            for (idx_t k = Tp[row - 1]; k < Tp[row]; k += 16) __builtin_prefetch(&Tj[k]);
+        }
+      }
+      const int64_t i6 = index_to_node[top_index - 1];
+      if (state[i6] != F_NODE) {
+        for (idx_t j = Sp[i6 - 1]; j < Sp[i6]; ++j) {
+          const int64_t row = (int64_t)Sj[j] + 1;
+          if (state[row] == U_NODE)
+            for (idx_t k = Tp[row - 1]; k < Tp[row]; ++k) __builtin_prefetch(&node[(int64_t)Tj[k] + 1]);
+        }
+      }
+    }
     const int64_t i = index_to_node[top_index];
-    const int64_t lambda_i = lambda[i] + 1;
+    const int64_t lambda_i = node[i].lambda + 1;
     interval_count[lambda_i] -= 1;
-    if (splitting[i - 1] == F_NODE) continue;
-    splitting[i - 1] = C_NODE;
+    if (state[i] == F_NODE) continue;
+    state[i] = C_NODE;
     for (idx_t j = Sp[i - 1]; j < Sp[i]; ++j) {
       const int64_t row = (int64_t)Sj[j] + 1;
-      if (splitting[row - 1] == U_NODE) {
-        splitting[row - 1] = F_NODE;
+      if (state[row] == U_NODE) {
+        state[row] = F_NODE;
         for (idx_t k = Tp[row - 1]; k < Tp[row]; ++k) {
           const int64_t rowk = (int64_t)Tj[k] + 1;
-          if (splitting[rowk - 1] == U_NODE) {
-            if (lambda[rowk] >= n - 1) continue;
-            const int64_t lambda_k = lambda[rowk] + 1;
-            const int64_t old_pos = node_to_index[rowk];
+          if (state[rowk] == U_NODE) {
+            NodeRec& nk = node[rowk];
+            if (nk.lambda >= n - 1) continue;
+            const int64_t lambda_k = nk.lambda + 1;
+            const int64_t old_pos = nk.pos;
             const int64_t new_pos = interval_ptr[lambda_k] + interval_count[lambda_k];
             const int64_t swap_node = index_to_node[new_pos];
             index_to_node[old_pos] = (bk_t)swap_node;
             index_to_node[new_pos] = (bk_t)rowk;
-            node_to_index[rowk] = (bk_t)new_pos;
-            node_to_index[swap_node] = (bk_t)old_pos;
-            lambda[rowk] += 1;
+            nk.pos = (bk_t)new_pos;
+            node[swap_node].pos = (bk_t)old_pos;
+            nk.lambda += 1;
             interval_count[lambda_k] -= 1;
             interval_count[lambda_k + 1] += 1;
             interval_ptr[lambda_k + 1] = (bk_t)(new_pos - 1);
@@ -292,23 +373,25 @@ int amgsetup_rs_cf_splitting(int64_t n_, const idx_t* Sp, const idx_t* Sj, const
     }
     for (idx_t j = Tp[i - 1]; j < Tp[i]; ++j) {
       const int64_t row = (int64_t)Tj[j] + 1;
-      if (splitting[row - 1] == U_NODE) {
-        if (lambda[row] == 0) continue;
-        const int64_t lambda_j = lambda[row] + 1;
-        const int64_t old_pos = node_to_index[row];
+      if (state[row] == U_NODE) {
+        NodeRec& nr = node[row];
+        if (nr.lambda == 0) continue;
+        const int64_t lambda_j = nr.lambda + 1;
+        const int64_t old_pos = nr.pos;
         const int64_t new_pos = interval_ptr[lambda_j] + 1;
         const int64_t swap_node = index_to_node[new_pos];
         index_to_node[old_pos] = (bk_t)swap_node;
         index_to_node[new_pos] = (bk_t)row;
-        node_to_index[row] = (bk_t)new_pos;
-        node_to_index[swap_node] = (bk_t)old_pos;
-        lambda[row] -= 1;
+        nr.pos = (bk_t)new_pos;
+        node[swap_node].pos = (bk_t)old_pos;
+        nr.lambda -= 1;
         interval_count[lambda_j] -= 1;
         interval_count[lambda_j - 1] += 1;
         interval_ptr[lambda_j] += 1;
       }
     }
   }
+  for (int64_t i = 1; i <= n; ++i) splitting[i - 1] = (idx_t)state[i];
   return 0;
 }
 
@@ -415,23 +498,38 @@ int64_t amgsetup_direct_interpolation(int64_t n, const idx_t* Ap, const idx_t* A
 // A: m x k, B: k x n.  Two-phase API: amgsetup_spgemm_begin computes into an internal
 // buffer and returns nnz; amgsetup_spgemm_fetch copies out and frees.
 // ---------------------------------------------------------------------------------------
+// Work distribution: the columns of C are cut into chunks of equal ESTIMATED work (products per column), the chunks are
+// handed out dynamically; a thread computes a chunk into its own scratch (kept between chunks and calls: no page faults, no
+// growth in the loop), then copies it into an exactly-sized block.  amgsetup_spgemm_fetch copies the blocks to their final
+// place on all cores.  The result does not depend on the team size or on which thread computed which chunk.
+struct SpgemmChunk {
+  int64_t c0 = 0, c1 = 0, nnz = 0;
+  idx_t* rows = nullptr;
+  double* vals = nullptr;
+};
 struct SpgemmResult {
-  std::vector<std::vector<idx_t>> rows;   // per thread chunk
-  std::vector<std::vector<double>> vals;
+  std::vector<SpgemmChunk> chunks;
   std::vector<idx_t> colcount;            // per column
   int64_t n = 0, nnz = 0;
+  ~SpgemmResult() {
+    for (auto& c : chunks) { std::free(c.rows); std::free(c.vals); }
+  }
 };
 static SpgemmResult* g_spgemm = nullptr;
 static thread_local std::vector<double> tl_spgemm_acc;
-static thread_local std::vector<int64_t> tl_spgemm_mark;
-static thread_local int64_t tl_spgemm_stamp = 0;
+static thread_local std::vector<int32_t> tl_spgemm_mark;
+static thread_local int32_t tl_spgemm_stamp = 0;
+static thread_local std::vector<idx_t> tl_spgemm_rows;     // chunk scratch
+static thread_local std::vector<double> tl_spgemm_vals;
 
 // gives the per-thread accumulators back (call when a hierarchy is finished; the OpenMP pool threads persist)
 void amgsetup_spgemm_release(void) {
 #pragma omp parallel
   {
     std::vector<double>().swap(tl_spgemm_acc);
-    std::vector<int64_t>().swap(tl_spgemm_mark);
+    std::vector<int32_t>().swap(tl_spgemm_mark);
+    std::vector<idx_t>().swap(tl_spgemm_rows);
+    std::vector<double>().swap(tl_spgemm_vals);
     tl_spgemm_stamp = 0;
   }
 }
@@ -448,52 +546,94 @@ int64_t amgsetup_spgemm_begin(int64_t m, int64_t k, int64_t n, const idx_t* Ap, 
 #ifdef _OPENMP
   nthreads = omp_get_max_threads();
 #endif
-  R.rows.resize(nthreads);
-  R.vals.resize(nthreads);
-  // The runtime may deliver a SMALLER team than requested (OMP_DYNAMIC, OMP_THREAD_LIMIT, nested regions, cgroup limits):
-  // every thread that does run takes the chunks t, t + team, t + 2 team, ... so that all `nthreads` chunks are computed
-  // whatever the team size is (a chunk left out would silently leave empty columns in the Galerkin product).
-#pragma omp parallel num_threads(nthreads)
+  // products per column (an upper bound of the column's entries), as a running sum
+  std::vector<int64_t> work(n + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (int64_t j = 0; j < n; ++j) {
+    int64_t w = 0;
+    for (idx_t bp = Bp[j]; bp < Bp[j + 1]; ++bp) w += Ap[Bj[bp] + 1] - Ap[Bj[bp]];
+    work[j + 1] = w;
+  }
+  for (int64_t j = 0; j < n; ++j) work[j + 1] += work[j];
+  const int64_t total = work[n];
+  // ~32 chunks per thread, at least 256 products each
+  const int64_t per_chunk = std::max<int64_t>(256, total / std::max<int64_t>(1, (int64_t)nthreads * 32) + 1);
   {
-    int t0 = 0, team = 1;
-#ifdef _OPENMP
-    t0 = omp_get_thread_num();
-    team = omp_get_num_threads();
-#endif
-    for (int t = t0; t < nthreads; t += team) {
-    // contiguous static chunk of columns per thread so chunks concatenate in order
-    const int64_t c0 = n * t / nthreads, c1 = n * (t + 1) / nthreads;
-    // dense accumulator + marker per thread, kept between calls (a setup multiplies 2 x levels times): the marker
-    // holds "column + stamp" so nothing has to be cleared; only growth allocates
+    int64_t c0 = 0;
+    while (c0 < n) {
+      const int64_t target = work[c0] + per_chunk;
+      int64_t c1 = std::upper_bound(work.begin() + c0 + 1, work.begin() + n + 1, target) - work.begin();
+      c1 = std::min<int64_t>(std::max<int64_t>(c1 - 1, c0 + 1), n);
+      SpgemmChunk ch;
+      ch.c0 = c0;
+      ch.c1 = c1;
+      R.chunks.push_back(ch);
+      c0 = c1;
+    }
+  }
+  const int64_t nchunks = (int64_t)R.chunks.size();
+  int failed = 0;
+  const bool verbose = std::getenv("B200AMG_VERBOSE_SETUP") != nullptr;   // stage timers on stderr
+  const double t_begin = verbose ? wall_s() : 0.0;
+  double tc_sum = 0, tm_sum = 0;
+#pragma omp parallel num_threads(nthreads) reduction(+:tc_sum, tm_sum)
+  {
+    // dense accumulator + marker per thread, kept between calls (a setup multiplies 2 x levels times): the marker holds
+    // a per-thread column stamp so nothing has to be cleared; only growth allocates
     std::vector<double>& acc = tl_spgemm_acc;
-    std::vector<int64_t>& mark = tl_spgemm_mark;
-    int64_t& stamp = tl_spgemm_stamp;
-    if ((int64_t)acc.size() < m) { acc.resize(m); mark.assign(m, -1); stamp = 0; }
-    const int64_t base = stamp;          // marks of this call live in [base, base + n)
-    stamp += n + 1;
-    std::vector<idx_t> list;
-    std::vector<idx_t>& out_r = R.rows[t];
-    std::vector<double>& out_v = R.vals[t];
-    for (int64_t j = c0; j < c1; ++j) {
-      list.clear();
-      for (idx_t bp = Bp[j]; bp < Bp[j + 1]; ++bp) {
-        const idx_t kk = Bj[bp];
-        const double bv = Bx[bp];
-        for (idx_t ap = Ap[kk]; ap < Ap[kk + 1]; ++ap) {
-          const idx_t r = Aj[ap];
-          const double prod = Ax[ap] * bv;
-          if (mark[r] != base + j) { mark[r] = base + j; acc[r] = prod; list.push_back(r); }
-          else acc[r] += prod;
+    std::vector<int32_t>& mark = tl_spgemm_mark;
+    int32_t& stamp = tl_spgemm_stamp;
+    if ((int64_t)acc.size() < m) { acc.resize(m); mark.assign(m, 0); stamp = 0; }
+    std::vector<idx_t>& out_r = tl_spgemm_rows;
+    std::vector<double>& out_v = tl_spgemm_vals;
+#pragma omp for schedule(dynamic, 1)
+    for (int64_t c = 0; c < nchunks; ++c) {
+      SpgemmChunk& ch = R.chunks[c];
+      const int64_t bound = work[ch.c1] - work[ch.c0];
+      if ((int64_t)out_r.size() < bound) { out_r.resize(bound); out_v.resize(bound); }
+      idx_t* orow = out_r.data();
+      double* oval = out_v.data();
+      int64_t cnt = 0;
+      const double tq0 = verbose ? wall_s() : 0.0;
+      for (int64_t j = ch.c0; j < ch.c1; ++j) {
+        if (stamp == std::numeric_limits<int32_t>::max()) { std::fill(mark.begin(), mark.end(), 0); stamp = 0; }
+        ++stamp;
+        const int64_t first = cnt;
+        for (idx_t bp = Bp[j]; bp < Bp[j + 1]; ++bp) {
+          const idx_t kk = Bj[bp];
+          const double bv = Bx[bp];
+          for (idx_t ap = Ap[kk]; ap < Ap[kk + 1]; ++ap) {
+            const idx_t r = Aj[ap];
+            const double prod = Ax[ap] * bv;
+            if (mark[r] != stamp) { mark[r] = stamp; acc[r] = prod; orow[cnt++] = r; }
+            else acc[r] += prod;
+          }
+        }
+        std::sort(orow + first, orow + cnt);
+        for (int64_t q = first; q < cnt; ++q) oval[q] = acc[orow[q]];
+        R.colcount[j] = (idx_t)(cnt - first);
+      }
+      ch.nnz = cnt;
+      const double tq1 = verbose ? wall_s() : 0.0;
+      tc_sum += tq1 - tq0;
+      if (cnt > 0) {
+        ch.rows = (idx_t*)std::malloc(sizeof(idx_t) * cnt);
+        ch.vals = (double*)std::malloc(sizeof(double) * cnt);
+        if (!ch.rows || !ch.vals) {
+#pragma omp atomic write
+          failed = 1;
+        } else {
+          std::memcpy(ch.rows, orow, sizeof(idx_t) * cnt);
+          std::memcpy(ch.vals, oval, sizeof(double) * cnt);
         }
       }
-      std::sort(list.begin(), list.end());
-      for (idx_t r : list) { out_r.push_back(r); out_v.push_back(acc[r]); }
-      R.colcount[j] = (idx_t)list.size();
+      if (verbose) tm_sum += wall_s() - tq1;
     }
-    }   // chunks of this thread
   }
+  if (verbose) std::fprintf(stderr, "[amgsetup] spgemm %lld chunks: wall %.3f s, thread-seconds compute %.3f, block copy %.3f\n", (long long)nchunks, wall_s() - t_begin, tc_sum, tm_sum);
+  if (failed) { delete g_spgemm; g_spgemm = nullptr; return -3; }
   int64_t nnz = 0;
-  for (auto& v : R.rows) nnz += (int64_t)v.size();
+  for (auto& c : R.chunks) nnz += c.nnz;
   R.nnz = nnz;
   if (nnz > std::numeric_limits<idx_t>::max()) { delete g_spgemm; g_spgemm = nullptr; return -2; }
   return nnz;
@@ -504,15 +644,19 @@ int amgsetup_spgemm_fetch(idx_t* Cp, idx_t* Cj, double* Cx) {
   SpgemmResult& R = *g_spgemm;
   Cp[0] = 0;
   for (int64_t j = 0; j < R.n; ++j) Cp[j + 1] = Cp[j] + R.colcount[j];
-  int64_t off = 0;
-  for (size_t t = 0; t < R.rows.size(); ++t) {
-    if (!R.rows[t].empty()) {
-      std::memcpy(Cj + off, R.rows[t].data(), sizeof(idx_t) * R.rows[t].size());
-      std::memcpy(Cx + off, R.vals[t].data(), sizeof(double) * R.vals[t].size());
+  const int64_t nchunks = (int64_t)R.chunks.size();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t c = 0; c < nchunks; ++c) {
+    SpgemmChunk& ch = R.chunks[c];
+    if (ch.nnz > 0) {
+      const int64_t off = Cp[ch.c0];
+      std::memcpy(Cj + off, ch.rows, sizeof(idx_t) * ch.nnz);
+      std::memcpy(Cx + off, ch.vals, sizeof(double) * ch.nnz);
     }
-    off += (int64_t)R.rows[t].size();
-    std::vector<idx_t>().swap(R.rows[t]);
-    std::vector<double>().swap(R.vals[t]);
+    std::free(ch.rows);
+    std::free(ch.vals);
+    ch.rows = nullptr;
+    ch.vals = nullptr;
   }
   delete g_spgemm;
   g_spgemm = nullptr;

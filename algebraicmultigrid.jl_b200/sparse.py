@@ -18,7 +18,7 @@ IDX = np.int32
 class SparseMatrixCSC:
     """m x n sparse matrix: ``colptr`` (n+1), ``rowval`` (nnz, sorted per column), ``nzval`` (nnz)."""
 
-    __slots__ = ("m", "n", "colptr", "rowval", "nzval", "_bitsym", "eltype")
+    __slots__ = ("m", "n", "colptr", "rowval", "nzval", "_bitsym", "eltype", "_transpose_of")
 
     def __init__(self, m, n, colptr, rowval, nzval, eltype=None):
         self.m = int(m)
@@ -40,6 +40,7 @@ class SparseMatrixCSC:
         self.rowval = self.rowval[:nnz]
         self.nzval = self.nzval[:nnz]
         self._bitsym = None
+        self._transpose_of = None   # set by ``Classical``: the matrix this one is the (unmodified) transpose of
 
     # -- constructors -------------------------------------------------------------------
     @classmethod

@@ -11,7 +11,9 @@ class Classical:
 
     def __call__(self, at: SparseMatrixCSC):
         t = _hostlib.classical_strength(at, self.theta)
-        return t.transpose(), t
+        s = t.transpose()
+        s._transpose_of = t   # lets ``RS`` take S' from T's pattern instead of transposing S back
+        return s, t
 
 
 class SymmetricStrength:

@@ -51,7 +51,8 @@ enum {
   B200AMG_ERR_OOM = -6,
   B200AMG_ERR_STATE = -7,             /* call order violated (e.g. solve before finalize) */
   B200AMG_ERR_UNSUPPORTED = -8,
-  B200AMG_ERR_NO_DEVICE = -9          /* no CUDA device: there is NO CPU fallback */
+  B200AMG_ERR_NO_DEVICE = -9,         /* no CUDA device: there is NO CPU fallback */
+  B200AMG_ERR_CALLBACK = -10          /* the coarse-solver callback reported a failure */
 };
 
 /* smoother kinds — src/smoother.jl:18-23 (GaussSeidel), :92-99 (Jacobi), :173-180 (SOR) */
@@ -108,6 +109,16 @@ int32_t b200amg_add_level(b200amg_handle_t h, const b200amg_csc_t* A, const b200
  * QR/LU solvers (:66-81).  final_A is used when the hierarchy has no levels (multilevel.jl:167). */
 int32_t b200amg_set_coarse(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n,
                            const double* coarse_inverse_colmajor);
+/* The same with the coarse solver as a HOST CALLABLE — the reference's `coarse_solver(x, b)` is any callable
+ * (src/multilevel.jl:180,228; src/coarse_solver.jl:24-58 wraps LinearSolve factorisations, :66-81 a sparse QR), which is
+ * what a coarsest level too large for a dense operator needs (coarsening stopped at max_levels).  Per coarse solve the
+ * library copies coarse_b into pinned host memory, calls fn(user, n, 1, x_host, b_host) from a CUDA runtime thread in
+ * stream order (a host node when the cycle is a captured graph) and copies x back; fn must not call CUDA or this library
+ * on the same handle, returns 0 on success; a non-zero status surfaces as B200AMG_ERR_CALLBACK from the entry point that
+ * ran the cycle.  Use instead of b200amg_set_coarse. */
+typedef int32_t (*b200amg_coarse_fn)(void* user, int64_t n, int64_t ncols, double* x_host, const double* b_host);
+int32_t b200amg_set_coarse_callback(b200amg_handle_t h, const b200amg_csc_t* final_A, int64_t n,
+                                    b200amg_coarse_fn fn, void* user);
 /* Optional, BEFORE the first add_level: make this handle one rank (one process, one GPU) of a
  * hierarchy whose FINE level is split by contiguous row blocks over world_size ranks; coarser
  * levels live on rank 0.  Every rank then passes the SAME full hierarchy to add_level / set_coarse
