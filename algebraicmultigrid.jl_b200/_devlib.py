@@ -24,7 +24,7 @@ OP_A, OP_P, OP_R = 0, 1, 2
 # every symbol include/b200amg.h declares (tests check the library exports all of them)
 SYMBOLS = [
     "b200amg_last_error", "b200amg_version", "b200amg_device_count", "b200amg_create", "b200amg_add_level",
-    "b200amg_set_coarse", "b200amg_set_partition", "b200amg_finalize", "b200amg_destroy", "b200amg_solve",
+    "b200amg_set_coarse", "b200amg_set_coarse_callback", "b200amg_set_partition", "b200amg_finalize", "b200amg_destroy", "b200amg_solve",
     "b200amg_cycle", "b200amg_precond", "b200amg_smooth", "b200amg_apply", "b200amg_residual",
     "b200amg_coarse_solve", "b200amg_norm", "b200amg_pcg", "b200amg_smoother_create", "b200amg_smoother_apply",
     "b200amg_smoother_destroy", "b200amg_num_levels", "b200amg_level_info", "b200amg_launch_count",
@@ -81,6 +81,7 @@ def lib():
             "b200amg_create": [C.POINTER(vp), i32],
             "b200amg_add_level": [vp, pcsc, pcsc, pcsc, psm, psm, i32],
             "b200amg_set_coarse": [vp, pcsc, i64, vp],
+            "b200amg_set_coarse_callback": [vp, pcsc, i64, COARSE_FN, vp],
             "b200amg_set_partition": [vp, i32, i32, vp, i64],
             "b200amg_finalize": [vp],
             "b200amg_destroy": [vp],
@@ -275,6 +276,27 @@ def smoother_desc(config):
     return d
 
 
+COARSE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
+def _coarse_trampoline(cs):
+    """The C callback behind ``b200amg_set_coarse_callback``: wraps the pinned staging vectors as numpy arrays and calls the
+    host coarse solver ``cs(x, b)``; an exception becomes a non-zero status (B200AMG_ERR_CALLBACK at the entry point) and is
+    kept on the function object for the caller to inspect."""
+    def call(_user, n, ncols, xp, bp):
+        try:
+            shape = (n,) if ncols == 1 else (n, ncols)
+            x = np.ctypeslib.as_array(xp, shape=(n * ncols,)).reshape(shape, order="F")
+            b = np.ctypeslib.as_array(bp, shape=(n * ncols,)).reshape(shape, order="F")
+            cs(x, b)
+            return 0
+        except BaseException as e:   # never let an exception cross the C boundary
+            call.last_exception = e
+            return 1
+    call.last_exception = None
+    return call
+
+
 def _default_device():
     if "B200AMG_DEVICE" in os.environ:
         return int(os.environ["B200AMG_DEVICE"])
@@ -289,6 +311,7 @@ class DeviceHierarchy:
     def __init__(self, ml, device=None, partition=None, julia_indices=False):
         L = lib()
         self._h = C.c_void_p()
+        self._coarse_cb = None   # keeps the ctypes callback of a host coarse solver alive as long as the handle
         self.device = _default_device() if device is None else device
         _check(L.b200amg_create(C.byref(self._h), self.device))
         keep = []
@@ -306,8 +329,15 @@ class DeviceHierarchy:
                 sym = SYMMETRY[lv.presmoother.symmetry_name]
                 _check(L.b200amg_add_level(self._h, C.byref(a), C.byref(p), C.byref(r), C.byref(pre), C.byref(post), sym))
             fa = csc_desc(ml.final_A, keep, julia_indices)
-            inv = np.ascontiguousarray(np.asarray(ml.coarse_solver.dense_operator(), dtype=np.float64).reshape(-1, order="F"))
-            _check(L.b200amg_set_coarse(self._h, C.byref(fa), ml.final_A.n, _ptr(inv)))
+            cs = ml.coarse_solver
+            op = cs.dense_operator() if hasattr(cs, "dense_operator") else None
+            if op is not None:
+                inv = np.ascontiguousarray(np.asarray(op, dtype=np.float64).reshape(-1, order="F"))
+                _check(L.b200amg_set_coarse(self._h, C.byref(fa), ml.final_A.n, _ptr(inv)))
+            else:
+                # any callable cs(x, b) (coarse_solver.jl:24-58): run on the host from inside the cycle
+                self._coarse_cb = COARSE_FN(_coarse_trampoline(cs))
+                _check(L.b200amg_set_coarse_callback(self._h, C.byref(fa), ml.final_A.n, self._coarse_cb, None))
             _check(L.b200amg_finalize(self._h))
         except Exception:
             L.b200amg_destroy(self._h)

@@ -9,21 +9,45 @@ from __future__ import annotations
 import numpy as np
 
 
-DENSE_LIMIT = 16384   # rows: the device applies the coarse solve as ONE dense operator (b200amg_set_coarse, include/b200amg.h)
+DENSE_LIMIT = 16384   # rows: up to here the device applies the coarse solve as ONE dense operator (b200amg_set_coarse)
 
 
 def _check_dense_limit(A, who):
-    """The reference keeps a sparse factorisation of the coarsest matrix (``coarse_solver.jl:66-81``) and works for any size;
-    here the host forms a dense n x n operator that the device applies, so a coarsest level beyond DENSE_LIMIT rows (coarsening
-    stopped early: ``max_levels`` reached, an empty ``P``) is refused with a clear message instead of exhausting memory."""
+    """``Pinv`` needs the dense n x n pseudo-inverse (``coarse_solver.jl:11``): a coarsest level beyond DENSE_LIMIT rows is
+    refused with a clear message instead of exhausting memory (use ``QRSolver`` / ``LinearSolveWrapper`` there)."""
     if A.m > DENSE_LIMIT:
         raise ValueError(f"{who}: the coarsest matrix has {A.m} rows; the dense coarse operator is limited to {DENSE_LIMIT} "
-                         "(raise max_levels / lower max_coarse so that coarsening continues)")
+                         "(raise max_levels / lower max_coarse so that coarsening continues, or use QRSolver / "
+                         "LinearSolveWrapper, which keep a sparse factorisation)")
 
 
 class CoarseSolver:
+    """``cs(x, b)`` (``multilevel.jl:180,228``).  Two ways to reach the device: ``dense_operator()`` returns the matrix whose
+    product is the solve (applied by a CUDA kernel), or ``None`` — then the object itself is called on the HOST from inside the
+    cycle (``b200amg_set_coarse_callback``: the reference's coarse solver is any callable, ``coarse_solver.jl:24-58``)."""
+
     def dense_operator(self):
         raise NotImplementedError
+
+    def __call__(self, x, b):
+        """In-place host apply, ``x .= cs(b)`` (one column or an n x m block)."""
+        op = self.dense_operator()
+        x[...] = op @ b
+        return x
+
+
+class _SparseLU:
+    """Sparse LU of a coarsest matrix too large for a dense operator (the reference keeps a sparse factorisation for ANY size,
+    ``coarse_solver.jl:35-42,66-81``; SPQR does not exist here, a nonsingular matrix gives the same solution)."""
+
+    def __init__(self, A):
+        import scipy.sparse.linalg as spl
+
+        self.lu = spl.splu(A.to_scipy().tocsc())
+
+    def solve_into(self, x, b):
+        x[...] = self.lu.solve(np.ascontiguousarray(b, dtype=np.float64))
+        return x
 
 
 class Pinv(CoarseSolver):
@@ -47,7 +71,11 @@ class QRSolver(CoarseSolver):
     solution) the minimum-norm operator ``pinv(A)`` is used instead — documented deviation."""
 
     def __init__(self, A):
-        _check_dense_limit(A, "QRSolver")
+        self.sparse = None
+        if A.m > DENSE_LIMIT:   # sparse factorisation, applied on the host from inside the cycle
+            self.op = None
+            self.sparse = _SparseLU(A)
+            return
         a = A.todense()
         n = a.shape[0]
         if n == 0:
@@ -65,6 +93,9 @@ class QRSolver(CoarseSolver):
     def dense_operator(self):
         return self.op
 
+    def __call__(self, x, b):
+        return self.sparse.solve_into(x, b) if self.sparse is not None else super().__call__(x, b)
+
     def __repr__(self):
         return "QRSolver"
 
@@ -74,12 +105,19 @@ class LinearSolveWrapperInternal(CoarseSolver):
         import scipy.sparse.linalg as spl
 
         self.alg = alg
-        _check_dense_limit(A, "LinearSolveWrapper")
+        self.sparse = None
+        if A.m > DENSE_LIMIT:
+            self.op = None
+            self.sparse = _SparseLU(A)
+            return
         lu = spl.splu(A.to_scipy().tocsc())
         self.op = lu.solve(np.eye(A.n)) if A.n else np.zeros((0, 0))
 
     def dense_operator(self):
         return self.op
+
+    def __call__(self, x, b):
+        return self.sparse.solve_into(x, b) if self.sparse is not None else super().__call__(x, b)
 
     def __repr__(self):
         return str(self.alg)

@@ -37,6 +37,19 @@ cyclecode(::V) = Int32(0); cyclecode(::W) = Int32(1); cyclecode(::F) = Int32(2)
 
 check(rc) = rc == 0 || error("b200amg error $rc: " * unsafe_string(ccall((:b200amg_last_error, lib), Cstring, ())))
 
+const DENSE_COARSE_LIMIT = 16384
+const COARSE_SOLVERS = Dict{Ptr{Cvoid},Any}()      # handle => the hierarchy's coarse solver (kept alive for the callback)
+
+"""C callback of `b200amg_set_coarse_callback`: `coarse_solver(x, b)` (src/multilevel.jl:180,228) on the staging vectors."""
+function coarse_trampoline(user::Ptr{Cvoid}, n::Int64, ncols::Int64, x::Ptr{Float64}, b::Ptr{Float64})::Int32
+    try
+        COARSE_SOLVERS[user](unsafe_wrap(Array, x, n), unsafe_wrap(Array, b, n))
+        return Int32(0)
+    catch
+        return Int32(1)
+    end
+end
+
 """Device-resident copy of a `MultiLevel`: upload once, reuse for every solve."""
 mutable struct DeviceMultiLevel
     handle::Ptr{Cvoid}
@@ -56,13 +69,22 @@ function DeviceMultiLevel(ml::MultiLevel, pre::Smoother = GaussSeidel(), post::S
                         h[], a, p, r, Ref(desc(pre)), Ref(desc(post)), symmetry))
         end
         n = size(ml.final_A, 1)
-        Minv = Matrix(pinv(Matrix(ml.final_A)))      # Pinv (coarse_solver.jl:9-16); inv(A) for the QR/LU solvers
-        check(ccall((:b200amg_set_coarse, lib), Int32, (Ptr{Cvoid}, Ref{CscDesc}, Int64, Ptr{Float64}),
-                    h[], Ref(csc(ml.final_A)), n, Minv))
+        if n <= DENSE_COARSE_LIMIT
+            Minv = Matrix(pinv(Matrix(ml.final_A)))  # Pinv (coarse_solver.jl:9-16); inv(A) for the QR/LU solvers
+            check(ccall((:b200amg_set_coarse, lib), Int32, (Ptr{Cvoid}, Ref{CscDesc}, Int64, Ptr{Float64}),
+                        h[], Ref(csc(ml.final_A)), n, Minv))
+        else
+            # a coarsest level too large for a dense operator: the reference's own callable (sparse QR / LinearSolve
+            # factorisation, coarse_solver.jl:24-58,66-81) runs on the host from inside the cycle
+            COARSE_SOLVERS[h[]] = ml.coarse_solver
+            check(ccall((:b200amg_set_coarse_callback, lib), Int32, (Ptr{Cvoid}, Ref{CscDesc}, Int64, Ptr{Cvoid}, Ptr{Cvoid}),
+                        h[], Ref(csc(ml.final_A)), n,
+                        @cfunction(coarse_trampoline, Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Ptr{Float64})), h[]))
+        end
     end
     check(ccall((:b200amg_finalize, lib), Int32, (Ptr{Cvoid},), h[]))
     d = DeviceMultiLevel(h[], ml, isempty(ml.levels) ? size(ml.final_A, 1) : size(ml.levels[1].A, 1))
-    finalizer(x -> ccall((:b200amg_destroy, lib), Int32, (Ptr{Cvoid},), x.handle), d)
+    finalizer(x -> (delete!(COARSE_SOLVERS, x.handle); ccall((:b200amg_destroy, lib), Int32, (Ptr{Cvoid},), x.handle)), d)
     return d
 end
 

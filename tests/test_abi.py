@@ -79,3 +79,47 @@ def test_null_and_state_errors(amg):
     assert L.b200amg_finalize(None) == -1
     assert L.b200amg_destroy(None) == 0
     assert L.b200amg_num_levels(None) == 0
+
+
+def test_coarse_solver_host_callable_logic(amg, monkeypatch):
+    """Host side of b200amg_set_coarse_callback (no GPU needed): above the dense limit QRSolver / LinearSolveWrapper keep a
+    sparse factorisation (the reference does for any size, coarse_solver.jl:35-42,66-81) and are applied as callables;
+    Pinv refuses; the ctypes trampoline hands numpy views of the staging vectors to the callable and turns an exception
+    into a status instead of letting it cross the C boundary."""
+    import pytest
+
+    from algebraicmultigrid_jl_b200 import _devlib, coarse_solver as cs_mod
+
+    A = amg.poisson((12, 12))
+    dense = np.linalg.inv(A.todense())
+    b = np.random.default_rng(0).standard_normal(A.n)
+    monkeypatch.setattr(cs_mod, "DENSE_LIMIT", 100)
+    for make in (amg.QRSolver, amg.LinearSolveWrapper(amg.UMFPACKFactorization())):
+        cs = make(A)
+        assert cs.dense_operator() is None
+        x = np.empty(A.n)
+        cs(x, b)
+        assert np.abs(x - dense @ b).max() <= 1e-12 * np.abs(x).max()
+        X = np.empty((A.n, 3))
+        B3 = np.stack([b, 2 * b, -b], axis=1)
+        cs(X, B3)
+        assert np.abs(X - dense @ B3).max() <= 1e-11 * np.abs(X).max()
+    with pytest.raises(ValueError, match="dense coarse operator"):
+        amg.Pinv(A)
+    monkeypatch.setattr(cs_mod, "DENSE_LIMIT", 16384)
+    small = amg.QRSolver(A)
+    x = np.empty(A.n)
+    small(x, b)                                            # below the limit the callable form applies the dense operator
+    assert np.abs(x - small.dense_operator() @ b).max() == 0.0
+
+    # the trampoline: C pointers in, numpy views out, status back
+    fn = _devlib._coarse_trampoline(lambda xx, bb: xx.__setitem__(Ellipsis, 2.0 * bb))
+    cb = _devlib.COARSE_FN(fn)
+    xb, bb = (C.c_double * 5)(), (C.c_double * 5)(*range(5))
+    assert cb(None, 5, 1, xb, bb) == 0 and list(xb) == [0.0, 2.0, 4.0, 6.0, 8.0]
+
+    def boom(xx, bb):
+        raise RuntimeError("no factorisation")
+
+    fn = _devlib._coarse_trampoline(boom)
+    assert _devlib.COARSE_FN(fn)(None, 5, 1, xb, bb) == 1 and isinstance(fn.last_exception, RuntimeError)

@@ -825,3 +825,62 @@ def test_device_galerkin_product_is_bit_identical_to_host(amg, fx, monkeypatch):
         for lh, ld in zip(h_.levels, d_.levels):
             assert _same_csc(lh.A, ld.A)
         assert _same_csc(h_.final_A, d_.final_A)
+
+
+# ---- coarse solver as a host callable (coarse_solver.jl:24-58,66-81: any callable; sparse factorisation of ANY size) ---------
+def test_coarse_solver_as_host_callable(amg, monkeypatch):
+    """A coarsest level beyond the dense-operator limit (coarsening stopped at max_levels) is solved by a sparse LU on the
+    HOST from inside the cycle (b200amg_set_coarse_callback: D2H copy, host node, H2D copy — also inside the captured cycle
+    graph); the result must agree with the oracle run on the same hierarchy with the dense inverse.  A user callable works
+    the same way, and a failing callable surfaces as an error, never as a silent result."""
+    from algebraicmultigrid_jl_b200 import _devlib, coarse_solver as cs_mod
+
+    A = amg.poisson((24, 24, 24))
+    b = oracle.mul(A, np.ones(A.n))
+    ml_dense = amg.ruge_stuben(A, max_levels=2)                  # coarsest level: 6912 rows, dense inverse
+    nf = ml_dense.final_A.n
+    assert len(ml_dense.levels) == 1 and nf > 1000
+    xo, ro = oracle.OracleHierarchy(ml_dense).solve(b, log=True, maxiter=8)
+    monkeypatch.setattr(cs_mod, "DENSE_LIMIT", 1000)
+    for coarse in (None, amg.LinearSolveWrapper(amg.UMFPACKFactorization())):
+        kw = {} if coarse is None else {"coarse_solver": coarse}
+        ml = amg.ruge_stuben(A, max_levels=2, **kw)
+        assert ml.coarse_solver.dense_operator() is None         # sparse factorisation kept on the host
+        xd, rd = amg._solve(ml, b, log=True, maxiter=8)
+        assert len(rd) == len(ro)
+        assert np.abs(rd / ro - 1).max() <= TOL_HIST
+        assert np.linalg.norm(xd - xo) / np.linalg.norm(xo) <= TOL_SOLVE_X
+        # preconditioner application and the stand-alone coarse solve go through the same callable
+        dev = ml.device()
+        bf = _rng(4).standard_normal(nf)
+        assert relinf(dev.coarse_solve(np.empty(nf), bf), ml_dense.coarse_solver.dense_operator() @ bf) <= 1e-9
+        # W cycle: the coarse solve is reached once per visit of the last level
+        xw = amg._solve(ml, b, amg.W(), maxiter=3)
+        xwo = oracle.OracleHierarchy(ml_dense).solve(b, cycle="W", maxiter=3)
+        assert np.linalg.norm(xw - xwo) / np.linalg.norm(xwo) <= TOL_SOLVE_X
+    monkeypatch.setattr(cs_mod, "DENSE_LIMIT", 16384)
+
+    # any Python callable cs(x, b)
+    dense = np.linalg.inv(ml_dense.final_A.todense())
+    calls = []
+
+    class Mine:
+        def __init__(self, Ac):
+            pass
+
+        def __call__(self, x, bb):
+            calls.append(bb.shape)
+            x[...] = dense @ bb
+
+    ml = amg.ruge_stuben(A, max_levels=2, coarse_solver=Mine)
+    xd = amg._solve(ml, b, maxiter=8)
+    assert calls and calls[0] == (nf,)
+    assert np.linalg.norm(xd - xo) / np.linalg.norm(xo) <= TOL_SOLVE_X
+
+    class Broken(Mine):
+        def __call__(self, x, bb):
+            raise RuntimeError("factorisation lost")
+
+    ml = amg.ruge_stuben(A, max_levels=2, coarse_solver=Broken)
+    with pytest.raises(_devlib.B200AmgError, match="callback"):
+        amg._solve(ml, b, maxiter=2)
