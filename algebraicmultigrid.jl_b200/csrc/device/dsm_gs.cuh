@@ -348,4 +348,217 @@ __global__ void __launch_bounds__(BS + 32, 1)
   for (int i = tid; i < nslots; i += kDsmBlock) x[__ldg(rowof + off0 + i)] = xs[i];
 }
 
+
+// =============================================================================================
+// gs_dsm2_kernel: the same sweep on the same plan with TWO consumer groups that alternate the tiles of a CTA.
+// In gs_dsm_kernel everything between two wavefront hand-offs is serial in the same warps: stage wait, row pointers,
+// column codes / values out of the ring, gather addresses (a table lookup per entry), diagonal search — and only then the
+// gather, the sum, the division and the store that the NEXT wavefront is waiting for.  Here the group that owns tile
+// i + 1 does all of that PREPARATION (including the lane reduction that finds the diagonal) while the other group relaxes
+// tile i; what remains between two hand-offs is: gather burst -> products -> lane reduction -> division -> store.
+//   one CTA    hand-off = split named barrier: the relaxing group `bar.arrive`s right after its stores and goes on to prepare
+//              its next tile, the other group `bar.sync`s right before its gather (PTX producer / consumer pattern);
+//   NC > 1     hand-off = the per-wavefront mbarriers of gs_dsm_kernel (remote arrive by the first warp of the group after
+//              a group barrier); tiles of one CTA need no extra ordering: a tile of wavefront w waits for ALL tiles of
+//              wavefront w - 1, local ones included.
+// Stage s of the ring is always used by group s % 2 (kDsmStages is even), so the stage-release barrier 2 + s pairs that
+// group with the producer warp.  Named barriers: 0 __syncthreads, 2..7 stage release, 8 / 9 group hand-off, 10 / 11 group
+// barrier (NC > 1).
+// =============================================================================================
+static_assert(kDsmStages % 2 == 0, "gs_dsm2_kernel pairs stage parity with the consumer group");
+
+template <int LOG_NC, int T, int BS>
+__global__ void __launch_bounds__(2 * BS + 32, 1)
+    gs_dsm2_kernel(int n, int ntiles, int nlev, const int4* __restrict__ meta, const int2* __restrict__ aux,
+                   const int* __restrict__ rowptr, const int* __restrict__ code, const double* __restrict__ val,
+                   const int* __restrict__ rowof, const int* __restrict__ own_off, const int* __restrict__ wave_tiles, double* x,
+                   const double* __restrict__ b, double omega, int sor, int backward, int opaque_zero, int flags,
+                   int* __restrict__ status, unsigned long long* __restrict__ dbg) {
+  constexpr int NC = 1 << LOG_NC;
+  constexpr bool LOCAL = NC == 1;
+  constexpr int kCons = 2 * BS, kBlock = 2 * BS + 32, kRelease = BS + 32;
+  extern __shared__ __align__(128) unsigned char dsm_smem[];
+  DsmStage* st = reinterpret_cast<DsmStage*>(dsm_smem);
+  double* xs = reinterpret_cast<double*>(dsm_smem + kDsmStages * sizeof(DsmStage));
+  __shared__ __align__(8) uint64_t full[kDsmStages];    // stage filled (TMA bytes landed)
+  __shared__ uint32_t xaddr[NC];     // shared::cluster address of every CTA's x slots
+  __shared__ uint32_t wbaddr[NC];    // shared::cluster address of every CTA's wavefront barriers
+  __shared__ double s_zero;          // what idle slots of a gather burst read
+  const int tid = threadIdx.x;
+  const int grp = tid / BS;          // 0 / 1: consumer groups, 2: producer warp
+  const int gt = tid - grp * BS, g = gt / T, lane = gt % T;
+  unsigned rank = 0;
+  if (NC > 1) rank = cg::this_cluster().block_rank();
+  const int off0 = __ldg(own_off + rank), nslots = __ldg(own_off + rank + 1) - off0;
+  const int slots_max = __ldg(own_off + NC + 1);   // the same layout in every CTA
+  uint64_t* wb = reinterpret_cast<uint64_t*>(xs + slots_max);
+  const uint32_t wb0 = smem_u32(wb), zaddr = smem_u32(&s_zero);
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kDsmStages; ++s) mbar_init(&full[s], 1);
+    s_zero = 0.0;
+  }
+  if (NC > 1)
+    for (int i = tid; i < nlev; i += kBlock) mbar_init(&wb[i], (uint32_t)__ldg(wave_tiles + i));
+  mbar_fence_init();
+  __syncthreads();
+  const int nown = ntiles > (int)rank ? (ntiles - (int)rank + NC - 1) >> LOG_NC : 0;   // my tiles: rank, rank + NC, ...
+  auto tile_of = [&](int i) { return (int)rank + ((backward ? nown - 1 - i : i) << LOG_NC); };
+#pragma unroll 4
+  for (int i = tid; i < nslots; i += kBlock) xs[i] = __ldcg(x + __ldg(rowof + off0 + i));
+  if (tid < NC) {
+    xaddr[tid] = NC > 1 ? dsm_mapa(smem_u32(xs), (unsigned)tid) : smem_u32(xs);
+    wbaddr[tid] = NC > 1 ? dsm_mapa(wb0, (unsigned)tid) : wb0;
+  }
+  __syncthreads();
+  if (NC > 1) cg::this_cluster().sync();   // every CTA's x slots and barriers are initialised before anyone touches them
+
+  if (tid >= kCons) {
+    // ---- producer warp: keeps the ring full ----
+    int4 mt = nown > 0 ? __ldg(meta + tile_of(0)) : make_int4(0, 0, 0, 0);
+    int ps = 0;
+    for (int i = 0; i < nown; ++i) {
+      const int4 mn = i + 1 < nown ? __ldg(meta + tile_of(i + 1)) : mt;
+      if (i >= kDsmStages) asm volatile("bar.sync %0, %1;" ::"r"(2 + ps), "n"(kRelease) : "memory");   // released by the stage's group
+      if (tid == kCons) dsm_issue(st[ps], &full[ps], mt, rowptr, code, val, b);
+      mt = mn;
+      if (++ps == kDsmStages) ps = 0;
+    }
+  } else {
+    bool dead = false;
+    int4 m = make_int4(0, 0, 0, 0);
+    int2 au = make_int2(0, 0);
+    if (grp < nown) { m = __ldg(meta + tile_of(grp)); au = __ldg(aux + tile_of(grp)); }
+    for (int i = grp; i < nown; i += 2) {
+      const int s = i % kDsmStages;
+      const uint32_t parity = (uint32_t)(i / kDsmStages) & 1u;
+      int4 m_next = m;
+      int2 au_next = au;
+      if (i + 2 < nown) { m_next = __ldg(meta + tile_of(i + 2)); au_next = __ldg(aux + tile_of(i + 2)); }
+      unsigned long long* stamp = (dbg && gt == 0) ? dbg + 8 * (size_t)tile_of(i) : nullptr;   // diagnostics (gs_timeline)
+      if (stamp) stamp[0] = (unsigned long long)clock64();
+      // ---------------- PREPARE (overlaps the other group's relaxation) ----------------
+      const int wf = au.x;                            // forward wavefront number
+      const int wprev = backward ? wf + 1 : wf - 1;   // the wavefront the sweep relaxed before this one
+      const int ka = m.z & ~3, ra = m.x & ~3;
+      const int nrows = m.y - m.x;
+      const bool active = g < nrows;
+      const int row = active ? m.x + g : -1;
+      const int mycode = active ? (((au.y + g) << LOG_NC) | (int)rank) : -1;
+      mbar_wait(&full[s], parity);
+      const DsmStage& S = st[s];
+      int ks = 0, ke = 0;
+      if (active) {
+        ks = S.rp[row - ra] - ka;
+        ke = S.rp[row - ra + 1] - ka;
+      }
+      double v[kDsmBurst];
+      uint32_t a[kDsmBurst];
+      double d = 0.0;
+#pragma unroll
+      for (int j = 0; j < kDsmBurst; ++j) {
+        const int k = ks + lane + j * T;
+        const bool in = k < ke;
+        const int c = in ? S.col[k] : -1;
+        const double vv = in ? S.val[k] : 0.0;
+        const bool diag = c == mycode && c >= 0;
+        if (diag) d = vv;
+        const bool off = c >= 0 && !diag;
+        v[j] = off ? vv : 0.0;                      // the diagonal and idle slots contribute 0 * 0
+        a[j] = off ? xaddr[c & (NC - 1)] + 8u * (uint32_t)(c >> LOG_NC) : zaddr;
+      }
+      const bool long_row = ke - ks > kDsmBurst * T;   // entries beyond the first burst are handled after the hand-off
+      const bool any_long = __any_sync(0xffffffffu, long_row);
+      if (T > 1 && !any_long) d = group_lanes_sum<T>(d, 0xffffffffu);   // the diagonal is known before the hand-off
+      const double bi = (active && lane == 0) ? S.b[row - ra] : 0.0;
+      volatile double* slot = xs + (au.y + (active ? g : 0));   // my own shared memory
+      if (stamp) stamp[1] = (unsigned long long)clock64();
+      // ---------------- WAIT: the previous tile / wavefront has been relaxed ----------------
+      if (NC == 1) {
+        if (i > 0) asm volatile("bar.sync %0, %1;" ::"r"(8 + ((i - 1) & 1)), "n"(kCons) : "memory");
+      } else if (wprev >= 0 && wprev < nlev && !dead) {
+        const uint32_t ba = wb0 + 8u * (uint32_t)wprev;
+        long long t0 = 0;
+        unsigned spins = 0;
+        while (!((flags & 4) ? dsm_try_wait(ba, 0u) : dsm_test_wait(ba, 0u))) {
+          if ((++spins & 0x3ffu) == 0u) {   // watchdog: a protocol error must not hang the device
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 6000000000ll) { dead = true; if (status) atomicExch(status, 1); break; }
+          }
+        }
+        if (flags & 2) dsm_fence_cluster();
+      }
+      if (stamp) stamp[2] = (unsigned long long)clock64();
+      // ---------------- RELAX: gather burst, two partial sums per lane, lane reduction, division, store ----------------
+      double rs0 = 0.0, rs1 = 0.0;
+      {
+        double xn[kDsmBurst];
+        dsm_burst8<LOCAL>(xn, a);
+        pin_burst8(xn, opaque_zero);
+        if (stamp) stamp[3] = (unsigned long long)clock64() + (unsigned long long)(__double2loint(xn[0]) & opaque_zero);
+#pragma unroll
+        for (int j = 0; j < kDsmBurst; j += 2) {
+          rs0 = __dadd_rn(rs0, __dmul_rn(v[j], xn[j]));
+          rs1 = __dadd_rn(rs1, __dmul_rn(v[j + 1], xn[j + 1]));
+        }
+      }
+      if (any_long) {
+        for (int k0 = ks + kDsmBurst * T; k0 < ke; k0 += kDsmBurst * T) {   // rows longer than kDsmBurst * T entries
+          double xn[kDsmBurst];
+#pragma unroll
+          for (int j = 0; j < kDsmBurst; ++j) {
+            const int k = k0 + lane + j * T;
+            const bool in = k < ke;
+            const int c = in ? S.col[k] : -1;
+            const double vv = in ? S.val[k] : 0.0;
+            const bool diag = c == mycode && c >= 0;
+            if (diag) d = vv;
+            const bool off = c >= 0 && !diag;
+            v[j] = off ? vv : 0.0;
+            a[j] = off ? xaddr[c & (NC - 1)] + 8u * (uint32_t)(c >> LOG_NC) : zaddr;
+          }
+          dsm_burst8<LOCAL>(xn, a);
+          pin_burst8(xn, opaque_zero);
+#pragma unroll
+          for (int j = 0; j < kDsmBurst; j += 2) {
+            rs0 = __dadd_rn(rs0, __dmul_rn(v[j], xn[j]));
+            rs1 = __dadd_rn(rs1, __dmul_rn(v[j + 1], xn[j + 1]));
+          }
+        }
+        __syncwarp();   // lane groups of a warp may have walked different numbers of bursts
+        if (T > 1) d = group_lanes_sum<T>(d, 0xffffffffu);
+      }
+      double rsum = __dadd_rn(rs0, rs1);
+      if (T > 1) rsum = group_lanes_sum<T>(rsum, 0xffffffffu);
+      if (stamp) stamp[4] = (unsigned long long)clock64() + (unsigned long long)(__double2loint(rsum) & opaque_zero);
+      if (active && lane == 0 && d != 0.0) {
+        const double r = __dsub_rn(bi, rsum);
+        *slot = sor ? __dadd_rn(__dmul_rn(1.0 - omega, *slot), __dmul_rn(__ddiv_rn(omega, d), r)) : __ddiv_rn(r, d);
+      }
+      // ---------------- SIGNAL ----------------
+      if (NC == 1) {
+        if (i + 1 < nown) asm volatile("bar.arrive %0, %1;" ::"r"(8 + (i & 1)), "n"(kCons) : "memory");
+      } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(10 + grp), "n"(BS) : "memory");   // the tile's x is in my shared memory
+        if (gt < 32) {
+          if (flags & 1) dsm_fence_cluster();
+          else dsm_fence_cta();
+          if (gt < NC) dsm_arrive_remote(wbaddr[gt] + 8u * (uint32_t)wf);
+        }
+      }
+      if (stamp) { stamp[5] = (unsigned long long)clock64(); stamp[6] = stamp[5]; stamp[7] = global_ns(); }
+      if (i + kDsmStages < nown) asm volatile("bar.arrive %0, %1;" ::"r"(2 + s), "n"(kRelease) : "memory");   // stage s is free
+      m = m_next;
+      au = au_next;
+    }
+  }   // consumers
+  // nobody may leave (and release its shared memory) while others still gather from it
+  if (NC > 1) cg::this_cluster().sync();
+  else __syncthreads();
+#pragma unroll 4
+  for (int i = tid; i < nslots; i += kBlock) x[__ldg(rowof + off0 + i)] = xs[i];
+}
+
 }  // namespace b200amg

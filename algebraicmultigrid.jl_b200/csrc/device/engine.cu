@@ -583,7 +583,10 @@ struct SmootherMatrix {
     const bool multicolor = env_int("B200AMG_GS_MULTICOLOR", 0) != 0;
     const int block_mode = multicolor ? 0 : env_int("B200AMG_GS_BLOCK", 1);
     const double mean_row = n ? (double)hAt_in.nnz() / (double)n : 0.0;
-    const bool block_wanted = block_mode >= 2 || (block_mode == 1 && (mean_row <= 8.0 || n <= 1024));
+    // (tiny levels with longer rows: the two-group one-CTA sweep gs_dsm2_kernel is ahead of the blocked sweep — 800 / 181 / 51
+    // rows: 0.34 / 0.12 / 0.058 ms against 0.47 / 0.15 / 0.074 — so they only go to the blocked sweep when it is switched off)
+    const bool tiny_blocked = n <= 1024 && env_int("B200AMG_GS_DSM2", 1) == 0;
+    const bool block_wanted = block_mode >= 2 || (block_mode == 1 && (mean_row <= 8.0 || tiny_blocked));
     if ((need_fwd || need_bwd) && n > 0 && pattern_symmetric && block_wanted) {
       // blocked sweep: tiles of rows relaxed by one CTA each, rows renumbered (tile, local step, old index)
       const HostCsr& w0 = symmetry == B200AMG_SYMMETRY_HERMITIAN ? hAt_in : hA_in;
@@ -912,8 +915,10 @@ struct b200amg_hierarchy {
   int gs_cluster_log_nc = 3, gs_cluster_threads = 256;
   int gs_dsm = 1;                     // 1: one-cluster sweep with x in distributed shared memory + per-wavefront mbarriers
                                       // (dsm_gs.cuh) on narrow-wavefront levels that fit gs_dsm_max_log_nc CTAs; 2: required
-  int gs_dsm_max_log_nc = 2;          // measured (256^3 RS hierarchy, SGS ms): 1 CTA 2.56 -> 1.83 (5 195 rows), 4 CTAs
-                                      // 7.42 -> 5.63 (38 260 rows), 16 CTAs 4.69 -> 5.16 (228 538 rows): up to 4 CTAs by default
+  int gs_dsm_max_log_nc = 4;          // measured (256^3 RS hierarchy, SGS ms), gs_dsm_kernel: 1 CTA 2.56 -> 1.83 (5 195 rows), 4 CTAs
+                                      // 7.42 -> 5.63 (38 260 rows), 16 CTAs 4.69 -> 5.16 (228 538 rows); gs_dsm2_kernel: 1.29 / 4.71 /
+                                      // 3.75 -> up to 16 CTAs with the two-group kernel, up to 4 without it
+  int gs_dsm2 = 1;                    // 1: gs_dsm2_kernel (two consumer groups alternate the tiles: preparation off the hand-off path)
   int gs_dsm_fence = 0;               // bit 0 / 1: cluster-scope fence on the producer / consumer side of the hand-off
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
@@ -1283,8 +1288,37 @@ static int dsm_state() {
   }
   return state;
 }
+// the two-group variant (gs_dsm2_kernel): 2 x 256 consumer threads + the producer warp
+template <int LOG_NC, int T>
+static int dsm2_state() {
+  static int state = 0;
+  if (state != 0) return state;
+  constexpr int NC = 1 << LOG_NC;
+  cudaLaunchConfig_t probe = {};
+  probe.gridDim = dim3(NC, 1, 1);
+  probe.blockDim = dim3(2 * 256 + 32, 1, 1);
+  probe.dynamicSmemBytes = kDsmMaxDynSmem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = NC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  probe.attrs = attr;
+  probe.numAttrs = NC > 1 ? 1 : 0;
+  int nclusters = 1;
+  if (cudaFuncSetAttribute(gs_dsm2_kernel<LOG_NC, T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDsmMaxDynSmem) != cudaSuccess ||
+      (NC > 8 && cudaFuncSetAttribute(gs_dsm2_kernel<LOG_NC, T, 256>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+      (NC > 1 && (cudaOccupancyMaxActiveClusters(&nclusters, gs_dsm2_kernel<LOG_NC, T, 256>, &probe) != cudaSuccess || nclusters < 1))) {
+    cudaGetLastError();
+    state = -1;
+  } else {
+    state = 1;
+  }
+  return state;
+}
 template <int LOG_NC>
 static void dsm_init_nc() {
+  dsm2_state<LOG_NC, 4>(); dsm2_state<LOG_NC, 8>(); dsm2_state<LOG_NC, 16>(); dsm2_state<LOG_NC, 32>();
   dsm_state<LOG_NC, 4, 256>(); dsm_state<LOG_NC, 8, 256>(); dsm_state<LOG_NC, 16, 256>(); dsm_state<LOG_NC, 32, 256>();
   dsm_state<LOG_NC, 4, 512>(); dsm_state<LOG_NC, 8, 512>(); dsm_state<LOG_NC, 16, 512>(); dsm_state<LOG_NC, 32, 512>();
 }
@@ -1308,6 +1342,15 @@ static bool launch_gs_dsm_T(H* h, const SmootherMatrix& M, const DevCsr& A, cons
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = NC > 1 ? 1 : 0;
+  if (BS == 256 && h->gs_dsm2 && dsm2_state<LOG_NC, T>() > 0) {   // two consumer groups alternate the tiles (same plan)
+    cfg.blockDim = dim3(2 * 256 + 32, 1, 1);
+    CUDA_OK(cudaLaunchKernelEx(&cfg, gs_dsm2_kernel<LOG_NC, T, 256>, (int)M.n, M.dsm_ntiles, M.nlev, (const int4*)M.dsm_meta,
+                               (const int2*)M.dsm_aux, (const int*)A.ptr, (const int*)M.dsm_code, (const double*)A.val,
+                               (const int*)M.dsm_rowof, (const int*)M.dsm_own_off, (const int*)M.dsm_wave_tiles, x, b, w, sor,
+                               sc.backward, h->opaque_zero, h->gs_dsm_fence, M.dsm_status, h->gs_debug));
+    count_launch(h);
+    return true;
+  }
   CUDA_OK(cudaLaunchKernelEx(&cfg, gs_dsm_kernel<LOG_NC, T, BS>, (int)M.n, M.dsm_ntiles, M.nlev, (const int4*)M.dsm_meta,
                              (const int2*)M.dsm_aux, (const int*)A.ptr, (const int*)M.dsm_code, (const double*)A.val,
                              (const int*)M.dsm_rowof, (const int*)M.dsm_own_off, (const int*)M.dsm_wave_tiles, x, b, w, sor,
@@ -2138,8 +2181,10 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_counter_mail = env_int("B200AMG_GS_COUNTER_MAIL", 1);
   h->gs_cluster = env_int("B200AMG_GS_CLUSTER", 0);
   h->gs_dsm = env_int("B200AMG_GS_DSM", 1);
-  h->gs_dsm_max_log_nc = env_int("B200AMG_GS_DSM_MAX_CTAS_LOG2", 2);
+  h->gs_dsm2 = env_int("B200AMG_GS_DSM2", 1);
+  h->gs_dsm_max_log_nc = env_int("B200AMG_GS_DSM_MAX_CTAS_LOG2", h->gs_dsm2 ? 4 : 2);
   h->gs_dsm_fence = env_int("B200AMG_GS_DSM_FENCE", 0);
+
   h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_poll_masked = env_int("B200AMG_GS_POLL_MASKED", 1);
@@ -3290,6 +3335,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2: h->gs_dsm_max_log_nc = (int)value; break;
     case B200AMG_OPT_FP32_STORAGE: h->fp32_storage = value != 0; break;
     case 16: h->gs_poll_masked = (int)value; break;   // experiment knob (tools/tune_kernels.py)
+    case B200AMG_OPT_GS_DSM2: h->gs_dsm2 = (int)value; break;
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
       h->part_levels = std::max(1, (int)value);

@@ -274,7 +274,8 @@ enum { B200AMG_OPT_USE_GRAPHS = 0, B200AMG_OPT_TIME_RESIDUAL = 1, B200AMG_OPT_ST
        B200AMG_OPT_GS_GATE_SLEEP = 6, B200AMG_OPT_GS_CTA_ROWS = 7,
        B200AMG_OPT_GS_MAIL_MIN_WIDTH = 8, B200AMG_OPT_GS_CLUSTER = 9,
        B200AMG_OPT_PART_LEVELS = 12, B200AMG_OPT_GS_DSM = 13, B200AMG_OPT_GS_DSM_FENCE = 14, B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2 = 15,
-       B200AMG_OPT_FP32_STORAGE = 17 };
+       B200AMG_OPT_FP32_STORAGE = 17,
+       B200AMG_OPT_GS_DSM2 = 18 /* gs_dsm2_kernel: two consumer groups alternate the tiles of the one-cluster sweep */ };
 int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value);
 int32_t b200amg_residual_timings(b200amg_handle_t h, double* ms, int32_t cap, int32_t* n);
 /* Diagnostics: run one dataflow Gauss-Seidel sweep (forward / backward) of `level` on the level's

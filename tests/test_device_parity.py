@@ -737,13 +737,16 @@ def test_cluster_sweep_on_mid_size_level(amg):
 
 
 # ---- one-cluster sweep with x in distributed shared memory (csrc/device/dsm_gs.cuh) ----------------------
-@pytest.mark.parametrize("log_nc,fence", [(0, 0), (1, 0), (2, 0), (3, 0), (4, 0), (2, 3), (-1, 0)])
-def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence):
-    """Every cluster size (1..16 CTAs; -1 = chosen per level) of the distributed-shared-memory sweep gives the
-    reference's sequential Gauss-Seidel / SOR sweeps (forward, backward, symmetric; Hermitian and NoSymmetry walks),
-    on stencil rows, irregular RS coarse operators and a nonsymmetric matrix; then whole cycles through it."""
+@pytest.mark.parametrize("log_nc,fence,two_groups", [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0), (2, 3, 0), (-1, 0, 0),
+                                                     (0, 0, 1), (1, 0, 1), (2, 0, 1), (3, 0, 1), (4, 0, 1), (2, 3, 1), (-1, 0, 1)])
+def test_dsm_cluster_sweep_matches_oracle(amg, fx, monkeypatch, log_nc, fence, two_groups):
+    """Every cluster size (1..16 CTAs; -1 = chosen per level) of the distributed-shared-memory sweep — gs_dsm_kernel and the
+    two-group gs_dsm2_kernel — gives the reference's sequential Gauss-Seidel / SOR sweeps (forward, backward, symmetric;
+    Hermitian and NoSymmetry walks), on stencil rows, irregular RS coarse operators and a nonsymmetric matrix; then whole
+    cycles through it."""
     monkeypatch.setenv("B200AMG_GS_BLOCK", "0")
     monkeypatch.setenv("B200AMG_GS_DSM", "2")
+    monkeypatch.setenv("B200AMG_GS_DSM2", str(two_groups))
     monkeypatch.setenv("B200AMG_GS_DSM_MAX_CTAS_LOG2", "4")
     monkeypatch.setenv("B200AMG_GS_DSM_FENCE", str(fence))
     if log_nc >= 0:
