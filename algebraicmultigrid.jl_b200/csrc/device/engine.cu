@@ -542,6 +542,7 @@ struct SmootherMatrix {
   int4* gs_meta = nullptr;
   int* gs_tile_wave = nullptr;
   int gs_ntiles = 0, gs_lanes = 1;
+  mutable int gs_tile_ctas = 0;   // persistent CTAs of gs_tile_kernel chosen by tune_tile_ctas (0: all that fit)
   int* d_fwd_lvlptr = nullptr;   // forward wavefront boundaries (single-CTA sweep)
   int nlev = 0;
   bool pattern_symmetric = false;
@@ -923,9 +924,10 @@ struct b200amg_hierarchy {
   int gs_counter_mail = 1;            // counter sweep publishes mailboxes instead of fencing (symmetric patterns)
   int gs_tile_any_lanes = 1;          // 1: use the TMA-fed mailbox sweep for multi-lane rows too
   int64_t gs_mail_min_width = 1024;   // mean rows per wavefront from which the mailbox sweep is used
-  int gs_poll_masked = 1;             // TMA-fed mailbox sweep: 1 poll only the mailboxes a row still waits for (measured: -2.7 %);
-                                      // 2 additionally spin on one outstanding mailbox between rounds (B200AMG_GS_POLL_MASKED=2,
-                                      // parity-tested, not yet timed on hardware: opt-in)
+  int gs_poll_masked = -1;            // TMA-fed mailbox sweep: 1 poll only the mailboxes a row still waits for (measured: -2.7 %);
+                                      // 2 additionally spin on one outstanding mailbox between rounds; -1 (default): 2 on rows
+                                      // of >= 8 lanes, else 1 (measured, see launch_gs_tile_T)
+  int gs_tile_cta_limit = 0;          // experiment knob (B200AMG_GS_TILE_CTAS): cap on the persistent CTAs of gs_tile_kernel
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
   int gs_acquire = 0;     // consumer-side acquire of the dataflow sweep: 0 none (see stream.cuh), 1 ld.acquire, 2 fence
@@ -1196,12 +1198,17 @@ static int gs_tile_ctas() {
 template <int T>
 static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
                              int sor) {
-  const int ctas = std::min(M.gs_ntiles, gs_tile_ctas<T>());
+  int ctas = std::min(M.gs_ntiles, gs_tile_ctas<T>());
+  if (h->gs_tile_cta_limit > 0) ctas = std::min(ctas, h->gs_tile_cta_limit);   // experiment knob: fewer tiles in flight
+  else if (M.gs_tile_ctas > 0) ctas = std::min(ctas, M.gs_tile_ctas);          // measured at finalize (tune_tile_ctas)
+  // poll mode -1 (default): the focused spin pays on rows of >= 8 lanes (256^3 level 2: 5.82 -> 5.55 ms) and costs on
+  // 4-lane rows (level 1: 7.27 -> 7.90), profiles/r02_tile_knobs_256.log
+  const int poll_masked = h->gs_poll_masked >= 0 ? h->gs_poll_masked : (T >= 8 ? 2 : 1);
   gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(M.mail_ctl);
   count_launch(h);
   gs_tile_kernel<T><<<ctas, kGsTileThreads, kStages * sizeof(GsCtaStage), h->stream>>>(
       M.gs_ntiles, M.gs_meta, M.gs_tile_wave, M.nlev, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor, sc.backward, h->opaque_zero,
-      h->gs_poll_sleep, h->gs_gate_sleep, h->gs_poll_masked, h->gs_debug);
+      h->gs_poll_sleep, h->gs_gate_sleep, poll_masked, h->gs_debug);
   count_launch(h);
 }
 static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
@@ -2187,7 +2194,8 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
 
   h->gs_cluster_rows = env_int("B200AMG_GS_CLUSTER_ROWS", 380000);
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
-  h->gs_poll_masked = env_int("B200AMG_GS_POLL_MASKED", 1);
+  h->gs_poll_masked = env_int("B200AMG_GS_POLL_MASKED", -1);
+  h->gs_tile_cta_limit = env_int("B200AMG_GS_TILE_CTAS", 0);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
@@ -2667,6 +2675,63 @@ static void peer_setup(H* h) {
     fprintf(stderr, "[b200amg] rank %d: halo exchange over %s\n", me, h->peer.on ? "peer memory (CUDA IPC, direct stores into the neighbours' halos)" : "NCCL send/recv");
 }
 
+// does launch_sweep take the TMA-fed mailbox sweep (gs_tile_kernel) for this matrix?  (mirrors its selection)
+static bool sweep_uses_tile_kernel(const H* h, const SmootherMatrix& M) {
+  if (M.pass.ok || M.block.ok || M.n <= 0 || M.nlev <= 0) return false;
+  const bool wide = M.n / M.nlev >= h->gs_mail_min_width;
+  if (!wide) return false;
+  if (h->gs_mode >= 1 && M.n <= h->gs_cta_rows && M.walked().ntiles > 0 && M.d_fwd_lvlptr) return false;
+  return h->gs_mode == 2 && M.mail && M.gs_ntiles > 0 && (M.gs_lanes == 1 || h->gs_tile_any_lanes);
+}
+
+// How many persistent CTAs the mailbox sweep of a level gets.  MORE tiles in flight is not better: CTAs that hold tiles
+// several wavefronts ahead of the sweep's front only poll (issue slots and L2 bandwidth taken from the tiles on the critical
+// path of their SM).  Measured on B200, 256^3 RS hierarchy, SGS ms with 296 / 222 / 148 / 74 CTAs: level 0 (one lane per row)
+// 3.61 / 3.03 / 3.4 / 5.6, level 1 (4 lanes) 7.30 / 6.57 / 7.04 / 11.6, level 2 (8 lanes) 5.57 / 5.49 / 5.29 / 4.69
+// (profiles/r02_tile_cta_limit_256_scan.log) - the best count depends on the level, so it is MEASURED here, once per level,
+// on the level's own (zeroed) vectors.  The result of a sweep does not depend on it.  B200AMG_GS_TILE_TUNE=0 switches it off.
+static void tune_tile_ctas(H* h) {
+  if (h->world != 1 || !env_int("B200AMG_GS_TILE_TUNE", 1) || h->gs_tile_cta_limit > 0) return;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  for (size_t lvl = 0; lvl < h->levels.size(); ++lvl) {
+    Level& L = *h->levels[lvl];
+    const bool gs_pre = L.pre.kind == B200AMG_SMOOTHER_GS || L.pre.kind == B200AMG_SMOOTHER_SOR;
+    const bool gs_post = L.post.kind == B200AMG_SMOOTHER_GS || L.post.kind == B200AMG_SMOOTHER_SOR;
+    if (!(gs_pre || gs_post) || !sweep_uses_tile_kernel(h, L.M)) continue;
+    double* x = lvl == 0 ? h->x0 : h->levels[lvl - 1]->coarse_x;
+    double* b = lvl == 0 ? h->b0 : h->levels[lvl - 1]->coarse_b;
+    if (!x || !b || !L.temp) continue;
+    if (!e0) { CUDA_OK(cudaEventCreate(&e0)); CUDA_OK(cudaEventCreate(&e1)); }
+    const SmootherCfg& cfg = gs_pre ? L.pre : L.post;
+    CUDA_OK(cudaMemsetAsync(x, 0, sizeof(double) * (size_t)L.n, h->stream));
+    CUDA_OK(cudaMemsetAsync(b, 0, sizeof(double) * (size_t)L.n, h->stream));
+    const int full = std::min(L.M.gs_ntiles, 2 * h->num_sms);
+    int best = 0;
+    float best_ms = 0.f;
+    int worse_in_a_row = 0;
+    for (int eighths = 8; eighths >= 1 && worse_in_a_row < 2; --eighths) {
+      const int ctas = std::max(1, full * eighths / 8);
+      L.M.gs_tile_ctas = ctas;
+      float ms = 0.f;
+      for (int rep = 0; rep < 3; ++rep) {   // first one untimed
+        if (rep == 1) CUDA_OK(cudaEventRecord(e0, h->stream));
+        smooth(h, L.M, cfg, x, b, L.temp, false);
+      }
+      CUDA_OK(cudaEventRecord(e1, h->stream));
+      CUDA_OK(cudaEventSynchronize(e1));
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      if (best == 0 || ms < best_ms) { best = ctas; best_ms = ms; worse_in_a_row = 0; }
+      else ++worse_in_a_row;
+    }
+    L.M.gs_tile_ctas = best;
+    if (env_int("B200AMG_GS_TILE_TUNE_VERBOSE", 0))
+      std::fprintf(stderr, "[b200amg] level %zu: mailbox sweep on %d of %d CTAs (%.3f ms per smoother call)\n", lvl, best, full, best_ms / 2);
+  }
+  if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  sync_and_check(h);
+}
+
 int32_t b200amg_finalize(b200amg_handle_t h) {
   API_BEGIN
   REQUIRE(h, B200AMG_ERR_BAD_ARG, "null handle");
@@ -2690,6 +2755,7 @@ int32_t b200amg_finalize(b200amg_handle_t h) {
     CUDA_OK(cudaMemset(h->b0, 0, sizeof(double) * (size_t)(h->n0 + 8)));
   }
   h->finalized = true;
+  tune_tile_ctas(h);
   API_END
 }
 
@@ -3334,7 +3400,8 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_GS_DSM_FENCE: h->gs_dsm_fence = (int)value; break;
     case B200AMG_OPT_GS_DSM_MAX_CTAS_LOG2: h->gs_dsm_max_log_nc = (int)value; break;
     case B200AMG_OPT_FP32_STORAGE: h->fp32_storage = value != 0; break;
-    case 16: h->gs_poll_masked = (int)value; break;   // experiment knob (tools/tune_kernels.py)
+    case 16: h->gs_poll_masked = (int)value; break;   // experiment knobs (tools/tune_kernels.py, tools/tile_knobs.py)
+    case 19: h->gs_tile_cta_limit = (int)value; break;
     case B200AMG_OPT_GS_DSM2: h->gs_dsm2 = (int)value; break;
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");
