@@ -927,6 +927,7 @@ struct b200amg_hierarchy {
   int gs_poll_masked = -1;            // TMA-fed mailbox sweep: 1 poll only the mailboxes a row still waits for (measured: -2.7 %);
                                       // 2 additionally spin on one outstanding mailbox between rounds; -1 (default): 2 on rows
                                       // of >= 8 lanes, else 1 (measured, see launch_gs_tile_T)
+  int gs_gate_dist = 2;               // a tile of wavefront w stays off the mailboxes until wavefront w - gs_gate_dist has begun to finish
   int gs_tile_cta_limit = 0;          // experiment knob (B200AMG_GS_TILE_CTAS): cap on the persistent CTAs of gs_tile_kernel
   int gs_poll_sleep = 0, gs_gate_sleep = 100;   // ns between failed mailbox polls / throttle polls
   int opaque_zero = 0;    // a zero the compiler cannot see (scheduling fence in gs_dataflow_kernel)
@@ -1208,7 +1209,7 @@ static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, con
   count_launch(h);
   gs_tile_kernel<T><<<ctas, kGsTileThreads, kStages * sizeof(GsCtaStage), h->stream>>>(
       M.gs_ntiles, M.gs_meta, M.gs_tile_wave, M.nlev, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor, sc.backward, h->opaque_zero,
-      h->gs_poll_sleep, h->gs_gate_sleep, poll_masked, h->gs_debug);
+      h->gs_poll_sleep, h->gs_gate_sleep, poll_masked, std::max(1, h->gs_gate_dist), h->gs_debug);
   count_launch(h);
 }
 static void launch_gs_tile(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
@@ -2196,6 +2197,7 @@ int32_t b200amg_create(b200amg_handle_t* out, int32_t device) {
   h->gs_poll_sleep = env_int("B200AMG_GS_POLL_SLEEP", 0);
   h->gs_poll_masked = env_int("B200AMG_GS_POLL_MASKED", -1);
   h->gs_tile_cta_limit = env_int("B200AMG_GS_TILE_CTAS", 0);
+  h->gs_gate_dist = env_int("B200AMG_GS_GATE_DIST", 2);
   h->gs_gate_sleep = env_int("B200AMG_GS_GATE_SLEEP", 100);
   h->partial = dev_alloc<double>(kRedBlocks);
   h->scalars = dev_alloc<double>(16);
@@ -3402,6 +3404,7 @@ int32_t b200amg_set_option(b200amg_handle_t h, int32_t option, double value) {
     case B200AMG_OPT_FP32_STORAGE: h->fp32_storage = value != 0; break;
     case 16: h->gs_poll_masked = (int)value; break;   // experiment knobs (tools/tune_kernels.py, tools/tile_knobs.py)
     case 19: h->gs_tile_cta_limit = (int)value; break;
+    case 20: h->gs_gate_dist = (int)value; break;
     case B200AMG_OPT_GS_DSM2: h->gs_dsm2 = (int)value; break;
     case B200AMG_OPT_PART_LEVELS:
       REQUIRE(h->levels.empty(), B200AMG_ERR_STATE, "PART_LEVELS must be set before the first add_level");

@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
     gs_tile_kernel(int ntiles, const int4* __restrict__ meta, const int* __restrict__ tile_wave, int nlev, unsigned* ctl,
                    const int* __restrict__ rowptr, const int* __restrict__ col, const double* __restrict__ val, double* x,
                    const double* __restrict__ b, uint4* mail, double omega, int sor, int backward, int opaque_zero,
-                   int poll_sleep, int gate_sleep, int poll_masked, unsigned long long* __restrict__ dbg) {
+                   int poll_sleep, int gate_sleep, int poll_masked, int gate_dist, unsigned long long* __restrict__ dbg) {
   extern __shared__ __align__(128) unsigned char gs_tile_smem[];
   GsCtaStage* st = reinterpret_cast<GsCtaStage*>(gs_tile_smem);
   __shared__ __align__(8) uint64_t full[kStages];
@@ -956,9 +956,9 @@ __global__ void __launch_bounds__(kGsTileThreads, 2)
         }
         ldcg_burst8(xn, a);   // old values of later-ordered neighbours: in flight while we wait / poll below
       }
-      if (rbase == 0 && w >= 2) {   // throttle: stay off the mailboxes until wavefront w - 2 has begun to finish
+      if (rbase == 0 && w >= gate_dist) {   // throttle: stay off the mailboxes until wavefront w - gate_dist (2) has begun to finish
         if (tid == 0) {
-          const unsigned* hint = ctl + (size_t)w * kGsCounterStride;   // (2 + (w - 2))
+          const unsigned* hint = ctl + (size_t)(2 + w - gate_dist) * kGsCounterStride;
           while (ld_relaxed_u32(hint) != e)
             if (gate_sleep) __nanosleep(gate_sleep);
         }

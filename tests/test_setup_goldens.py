@@ -283,3 +283,52 @@ def test_elasticity_3d_generator(amg):
     assert np.linalg.matrix_rank(B) == 6
     ml = amg.smoothed_aggregation(A, B=B)
     assert len(ml.levels) >= 1 and ml.levels[0].P.shape[1] % 6 == 0
+
+
+def test_host_galerkin_product_and_splitting_shortcuts(amg, fx):
+    """The reworked host setup against independent computations: the chunked Galerkin product equals scipy's product
+    entry for entry (sorted rows, structural zeros kept, also with far more chunks than columns or threads), the
+    out-of-place `remove_diag!` equals the in-place statement of the reference (splitting.jl:8-18), and the C/F splitting
+    computed with S' taken from T's pattern equals the one computed with an explicit transpose."""
+    import scipy.sparse as sp
+
+    from algebraicmultigrid_jl_b200 import _hostlib
+
+    rng = np.random.default_rng(5)
+    for (m, k, n, da, db) in ((40, 30, 50, 0.2, 0.15), (7, 5, 3, 0.9, 0.9), (300, 300, 300, 0.02, 0.03), (5, 4, 0, 0.5, 0.5)):
+        Asp = sp.random(m, k, da, format="csc", random_state=rng)
+        Bsp = sp.random(k, n, db, format="csc", random_state=rng)
+        A, B = amg.SparseMatrixCSC.from_scipy(Asp), amg.SparseMatrixCSC.from_scipy(Bsp)
+        Cm = _hostlib.spgemm(A, B)
+        ref = (Asp @ Bsp).tocsc()
+        ref.sort_indices()
+        assert Cm.shape == (m, n)
+        for j in range(n):
+            rows = Cm.rowval[Cm.colptr[j]:Cm.colptr[j + 1]]
+            assert np.all(np.diff(rows) > 0)                                  # sorted, no duplicates
+        assert np.abs(Cm.to_scipy() - ref).max() <= 1e-14 if n else True
+        assert Cm.nnz >= ref.nnz                                              # structural zeros are kept, never dropped
+    # exact cancellation is KEPT as a stored zero (stdlib spmatmul semantics the nnz goldens rely on)
+    A = amg.SparseMatrixCSC.from_dense(np.array([[1.0, -1.0], [0.0, 2.0]]))
+    B = amg.SparseMatrixCSC.from_dense(np.array([[1.0], [1.0]]))
+    Cm = _hostlib.spgemm(A, B)
+    assert Cm.nnz == 2 and list(Cm.nzval) == [0.0, 2.0]
+
+    # remove_diag!: zero the diagonal, then dropzeros!
+    S = amg.SparseMatrixCSC.from_dense(np.array([[4.0, 1.0, 0.0], [2.0, 5.0, 3.0], [0.0, 7.0, 6.0]]))
+    S.nzval[1] = 0.0            # a stored zero off the diagonal goes as well
+    _hostlib.remove_diag(S)
+    assert list(S.colptr) == [0, 0, 2, 3] and list(S.rowval) == [0, 2, 1] and list(S.nzval) == [1.0, 7.0, 3.0]
+
+    # S' from T's pattern == explicit transpose, on an irregular strength matrix (RS coarse level) and a nonsymmetric one
+    ml = amg.ruge_stuben(amg.poisson((14, 14, 14)))
+    for At in (ml.levels[1].A, ml.levels[2].A, fx.sprand_plus_diag(300, 0.04, 4.0, seed=3)):
+        s1, t1 = amg.Classical(0.25)(At)
+        fast = amg.RS()(s1)
+        s2, _ = amg.Classical(0.25)(At)
+        s2._transpose_of = None
+        slow = amg.RS()(s2)
+        assert np.array_equal(fast, slow)
+        cp, rv = _hostlib.offdiag_pattern(t1)
+        tt = s2.transpose()                      # s2 had its diagonal removed by RS
+        assert np.array_equal(cp, tt.colptr) and np.array_equal(rv, tt.rowval)

@@ -40,6 +40,17 @@ for masked, poll_sleep, gate_sleep in configs:
 dev.set_option(16, -1)
 dev.set_option(5, 0)
 dev.set_option(6, 100)
+for dist in [int(v) for v in os.environ.get("GATE_DISTS", "").split(",") if v]:
+    dev.set_option(20, dist)
+    for ctas in [int(v) for v in os.environ.get("CTA_LIMITS", "0").split(",")]:
+        dev.set_option(19, ctas)
+        row = {}
+        for lv in levels:
+            info = dev.level_info(lv)
+            ms = dev.time_kernel(lv, 2, reps=args.reps)
+            row[lv] = {"sgs_ms": round(ms, 4), "us_per_wavefront": round(1e3 * ms / max(2 * info["wavefronts"], 1), 3)}
+        print(json.dumps({"gate_dist": dist, "cta_limit": ctas, "levels": row}), flush=True)
+dev.set_option(20, 2)
 for ctas in [int(v) for v in os.environ.get("CTA_LIMITS", "0,222,148,74,0").split(",")]:   # persistent CTAs of the sweep (0 = all that fit: 2 per SM): tiles in flight
     dev.set_option(19, ctas)
     row = {}
