@@ -36,6 +36,13 @@
 
 namespace b200amg {
 
+// sizes of gs_block_kernel's shared-memory stages (block_gs.cuh) that the plan is built for
+constexpr int kBgStageNnz = 1024;
+constexpr int kBgStageRows = 256;
+constexpr int kBgWindow = 2048;
+constexpr int kBgDepth = 5;
+
+
 struct BI4 { int x, y, z, w; };   // layout of CUDA's int4 / int2 (uploaded as such)
 struct BI2 { int x, y; };
 

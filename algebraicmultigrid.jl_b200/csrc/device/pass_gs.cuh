@@ -39,10 +39,8 @@ namespace b200amg {
 constexpr int kPgCompute = 2 * kPassGroup;
 constexpr int kPgThreads = kPgCompute + 64;   // + producer warp, gate / publisher warp
 constexpr int kPgSlots = 16;                  // passes in flight in the ring (power of two)
-constexpr int kPgRingBytes = 192 * 1024;      // slabs + right-hand side + diagonal of the passes in flight
 // one pass in the ring: values | indices | b | diagonal (entries = (far + near slots) * width; rows padded to an even count)
-constexpr int kPgWinOff = kPgRingBytes;       // byte offsets inside the dynamic shared memory
-constexpr int kPgZeroOff = kPgWinOff + kPassWindow * (int)sizeof(double);
+// (kPgRingBytes, kPgWinOff, kPgZeroOff: pass_plan.h — the near slots of the plan hold shared-memory byte offsets)
 constexpr int kPgSmemBytes = kPgZeroOff + 16;
 static_assert(kPgSmemBytes + 1024 <= 232448, "ring + window exceed the shared memory of one SM");
 static_assert((kPgSlots & (kPgSlots - 1)) == 0, "slot count must be a power of two");

@@ -34,6 +34,10 @@ constexpr int kPassNearSlots = 4;        // near slots per lane and pass (regist
 constexpr int kPassNear = 4;             // a value this many passes old (or younger) is read from the window
 constexpr int kPassWindow = 2048;        // x values of the tile kept in shared memory (power of two)
 static_assert(kPassWindow >= (kPassNear + 2) * kPassRows, "window too small");
+// layout of gs_pass_kernel's dynamic shared memory (pass_gs.cuh): byte ring of whole passes, then the x window, then a zero
+constexpr int kPgRingBytes = 192 * 1024;      // slabs + right-hand side + diagonal of the passes in flight
+constexpr int kPgWinOff = kPgRingBytes;       // byte offsets inside the dynamic shared memory
+constexpr int kPgZeroOff = kPgWinOff + kPassWindow * (int)sizeof(double);
 
 struct PassDir {              // one sweep direction, everything in SWEEP order
   std::vector<BI2> tile;      // per tile: {first pass, end pass}                                            (global indices)
