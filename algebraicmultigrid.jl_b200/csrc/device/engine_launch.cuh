@@ -132,7 +132,7 @@ static int gs_dataflow_ctas() {   // co-resident CTAs of the persistent dataflow
   if (!cached) {
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_dataflow_kernel<T, BS, MAIL>, BS, 0));
-    cached = std::max(1, per_sm) * kNumSM;
+    cached = std::max(1, per_sm);   // per SM: the call sites multiply by the SM count of the handle's device
   }
   return cached;
 }
@@ -141,13 +141,13 @@ static void launch_dataflow_T(H* h, const DevCsr& A, const DevSchedule& sc, doub
                               uint4* mail, unsigned* mail_ctl) {
   CUDA_OK(cudaMemsetAsync(sc.counters, 0, sizeof(unsigned) * (size_t)(sc.nlev + 2) * kGsCounterStride, h->stream));
   if (mail && h->gs_counter_mail && !h->gs_debug) {
-    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, true>());
+    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, true>() * h->num_sms);
     gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(mail_ctl);   // new epoch for the mailbox flags
     count_launch(h);
     gs_dataflow_kernel<T, BS, true><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
                                                                sc.backward, h->gs_acquire, h->opaque_zero, nullptr, mail, mail_ctl);
   } else {
-    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, false>());
+    const int ctas = std::min(sc.ntasks, gs_dataflow_ctas<T, BS, false>() * h->num_sms);
     gs_dataflow_kernel<T, BS, false><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, sc.counters, A.ptr, A.idx, A.val, x, b, w, sor,
                                                                 sc.backward, h->gs_acquire, h->opaque_zero, h->gs_debug, nullptr, nullptr);
   }
@@ -175,14 +175,14 @@ static int gs_mail_ctas() {
   if (!cached) {
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_mail_kernel<T, BS>, BS, 0));
-    cached = std::max(1, per_sm) * kNumSM;
+    cached = std::max(1, per_sm);   // per SM: the call sites multiply by the SM count of the handle's device
   }
   return cached;
 }
 template <int T, int BS>
 static void launch_mail_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
                           int sor) {
-  const int ctas = std::min(sc.ntasks, gs_mail_ctas<T, BS>());
+  const int ctas = std::min(sc.ntasks, gs_mail_ctas<T, BS>() * h->num_sms);
   gs_mail_prepare_kernel<<<1, 32, 0, h->stream>>>(M.mail_ctl);
   count_launch(h);
   gs_mail_kernel<T, BS><<<ctas, BS, 0, h->stream>>>(sc.ntasks, sc.tasks, M.mail_ctl, A.ptr, A.idx, A.val, x, b, M.mail, w, sor,
@@ -212,14 +212,14 @@ static int gs_tile_ctas() {
     CUDA_OK(cudaFuncSetAttribute(gs_tile_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kStages * sizeof(GsCtaStage))));
     int per_sm = 0;
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_tile_kernel<T>, kGsTileThreads, kStages * sizeof(GsCtaStage)));
-    cached = std::max(1, per_sm) * kNumSM;
+    cached = std::max(1, per_sm);   // per SM: the call sites multiply by the SM count of the handle's device
   }
   return cached;
 }
 template <int T>
 static void launch_gs_tile_T(H* h, const SmootherMatrix& M, const DevCsr& A, const DevSchedule& sc, double* x, const double* b, double w,
                              int sor) {
-  int ctas = std::min(M.gs_ntiles, gs_tile_ctas<T>());
+  int ctas = std::min(M.gs_ntiles, gs_tile_ctas<T>() * h->num_sms);
   if (h->gs_tile_cta_limit > 0) ctas = std::min(ctas, h->gs_tile_cta_limit);   // experiment knob: fewer tiles in flight
   else if (M.gs_tile_ctas > 0) ctas = std::min(ctas, M.gs_tile_ctas);          // measured at finalize (tune_tile_ctas)
   // poll mode -1 (default): the focused spin pays on rows of >= 8 lanes (256^3 level 2: 5.82 -> 5.55 ms) and costs on

@@ -9,7 +9,7 @@
 namespace b200amg {
 
 constexpr int kThreads = 256;
-constexpr int kNumSM = 148;
+constexpr int kNumSM = 148;   // B200; only sizes compile-time tables (kRedBlocks) — grids use the SM count queried at b200amg_create
 
 template <int T>
 __device__ __forceinline__ double group_sum(double v) {
