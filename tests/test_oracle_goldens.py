@@ -230,3 +230,57 @@ def test_loop_quirks(amg):
     # ldiv! == zero + one cycle
     b = np.arange(100.0)
     assert np.array_equal(H.precond(b), H.cycle(np.zeros(100), b))
+
+
+def test_user_assembled_geometric_hierarchy(amg):
+    """test/gmg.jl + test/runtests.jl:104-108: a hierarchy a USER assembles from the package's own pieces — `Level(A, P, R,
+    pre, post)` with an explicit linear-interpolation `P` (plain CSC), `R = adjoint(P)`, Galerkin `R*A*P`, `Pinv` on the
+    coarsest level — has `length(ml) == 10` on poisson(10^6); the oracle then cycles on it like on any other hierarchy."""
+    import oracle
+    from algebraicmultigrid_jl_b200 import _hostlib
+    from algebraicmultigrid_jl_b200.multilevel import coarse_b_, coarse_x_, residual_
+    from algebraicmultigrid_jl_b200.smoother import setup_smoother
+    from algebraicmultigrid_jl_b200.sparse import adjoint
+
+    def extend(levels, A, pre, post):
+        size_f = A.m
+        size_c = (size_f - 1) // 2 + 1 if size_f % 2 == 0 else (size_f - 1) // 2      # gmg.jl:25
+        k = np.arange(1, size_c + 1)
+        rows = [2 * k - 1]                                                              # I = 2k (1-based)
+        cols = [k - 1]
+        vals = [np.ones(size_c)]
+        k = np.arange(1, size_c)
+        rows += [2 * k, 2 * k]                                                          # I = 2k+1 -> columns k and k+1
+        cols += [k - 1, k]
+        vals += [np.full(size_c - 1, 0.5), np.full(size_c - 1, 0.5)]
+        import scipy.sparse as sp
+
+        P = amg.SparseMatrixCSC.from_scipy(sp.csc_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))),
+                                                         shape=(size_f, size_c)))
+        R = adjoint(P)
+        levels.append(amg.Level(A, P, R, setup_smoother(pre, A, amg.HermitianSymmetry()),
+                                setup_smoother(post, A, amg.HermitianSymmetry())))
+        Rm = P.transpose()
+        return _hostlib.spgemm(_hostlib.spgemm(Rm, A), P)
+
+    def multigrid(A, max_levels=10, max_coarse=10):
+        pre, post = amg.GaussSeidel(), amg.GaussSeidel()
+        levels = []
+        w = amg.MultiLevelWorkspace(1, np.dtype(np.float64))
+        while len(levels) + 1 < max_levels and A.m > max_coarse:
+            residual_(w, A.m)
+            A = extend(levels, A, pre, post)
+            coarse_x_(w, A.m)
+            coarse_b_(w, A.m)
+        return amg.MultiLevel(levels, A, amg.Pinv(A), pre, post, w)
+
+    ml = multigrid(amg.poisson(10 ** 6))
+    assert len(ml) == 10                                                                # runtests.jl:108
+    assert [lv.A.m for lv in ml.levels][:3] == [1000000, 500000, 250000]
+    # the same construction on a size the coarsest level resolves: the cycle converges to the solution
+    A = amg.poisson(1000)
+    ml = multigrid(A)
+    b = oracle.mul(A, np.ones(A.n))
+    x, hist = oracle.OracleHierarchy(ml).solve(b, log=True, reltol=1e-10)
+    assert hist[-1] <= 1e-10 * hist[0] and len(hist) < 40
+    assert np.abs(x - 1).max() < 1e-6
