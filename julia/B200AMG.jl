@@ -110,6 +110,25 @@ end
 AlgebraicMultigrid._solve(d::DeviceMultiLevel, b::Vector{Float64}, args...; kwargs...) =
     AlgebraicMultigrid._solve!(zeros(Float64, size(b)), d, b, args...; kwargs...)
 
+"""Block right-hand sides (`Val{bs}` workspaces, src/multilevel.jl:28-59; one Frobenius norm, :170,190): every column stays
+on the device for the whole call (`b200amg_solve_block`)."""
+function AlgebraicMultigrid._solve!(x::Matrix{Float64}, d::DeviceMultiLevel, b::Matrix{Float64}, cycle::Cycle = V();
+                                    maxiter::Int = 100, abstol::Real = zero(Float64), reltol::Real = sqrt(eps(Float64)),
+                                    log::Bool = false, calculate_residual = true, kwargs...)
+    size(x) == size(b) || throw(DimensionMismatch("x is $(size(x)), b is $(size(b))"))
+    residuals = Vector{Float64}(undef, maxiter + 2)
+    nres, iters = Ref{Int32}(0), Ref{Int32}(0)
+    check(ccall((:b200amg_solve_block, lib), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Int64, Int64, Int32, Int32, Float64, Float64, Int32, Ptr{Float64}, Int32,
+                 Ref{Int32}, Ref{Int32}, Int32),
+                d.handle, x, b, size(b, 2), stride(b, 2), cyclecode(cycle), maxiter, abstol, reltol, calculate_residual ? 1 : 0,
+                residuals, length(residuals), nres, iters, 0))
+    resize!(residuals, nres[])
+    return log ? (x, residuals) : x
+end
+AlgebraicMultigrid._solve(d::DeviceMultiLevel, b::Matrix{Float64}, args...; kwargs...) =
+    AlgebraicMultigrid._solve!(zeros(Float64, size(b)), d, b, args...; kwargs...)
+
 """`ldiv!(x, p, b)` (src/preconditioner.jl:12-19): x .= 0 (or b), one cycle, no residual."""
 struct DevicePreconditioner{C<:Cycle}
     d::DeviceMultiLevel
