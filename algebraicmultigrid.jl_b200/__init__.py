@@ -11,7 +11,7 @@ points raise.
 from . import _hostlib
 from ._hostlib import set_galerkin_backend
 from .aggregate import StandardAggregation
-from .aggregation import JacobiProlongation, fit_candidates, smoothed_aggregation
+from .aggregation import DiagonalWeighting, JacobiProlongation, LocalWeighting, fit_candidates, smoothed_aggregation
 from .classical import direct_interpolation, ruge_stuben
 from .coarse_solver import LinearSolveWrapper, Pinv, QRSolver, UMFPACKFactorization
 from .gallery import elasticity_2d, elasticity_3d, poisson
@@ -23,6 +23,6 @@ from .smoother import (SOR, BackwardSweep, ForwardSweep, GaussSeidel, Jacobi, Si
 from .sparse import Adjoint, SparseMatrixCSC, adjoint, nnz, size
 from .splitting import RS
 from .strength import Classical, SymmetricStrength
-from .utils import Hermitian, HermitianSymmetry, NoSymmetry, Symmetric
+from .utils import Hermitian, HermitianSymmetry, NoSymmetry, Symmetric, approximate_spectral_radius
 
 __all__ = [n for n in dir() if not n.startswith("__")]

@@ -21,17 +21,38 @@ class LocalWeighting:
     pass
 
 
+def _diagonal_weight(A, omega):
+    """``weight(::DiagonalWeighting, S, ω)`` (``aggregation.jl:19-24``): ``(ω / ρ(D⁻¹S)) D⁻¹S`` with D = diag(S) and ρ the
+    approximate spectral radius (random start vector: the prolongator is not bit-reproducible, as in the reference)."""
+    from .utils import approximate_spectral_radius
+
+    n = A.n
+    cols = np.repeat(np.arange(n), np.diff(A.colptr))
+    diag = np.zeros(n)
+    on_diag = A.rowval == cols
+    diag[A.rowval[on_diag]] = A.nzval[on_diag]
+    with np.errstate(divide="ignore"):
+        d_inv = 1.0 / diag                                         # 1 ./ diag(S): Inf where the diagonal is missing, like Julia
+    scaled = SparseMatrixCSC(A.m, A.n, A.colptr.copy(), A.rowval.copy(), A.nzval * d_inv[A.rowval])   # scale_rows
+    rho = approximate_spectral_radius(scaled)
+    scaled.nzval *= omega / rho
+    return scaled
+
+
 class JacobiProlongation:
-    """``JacobiProlongation(ω)`` (``aggregation.jl:1-17``): ``P = T - (ω D^-1 A) T`` with LocalWeighting,
-    D = row sums of |A| (``:26-47``)."""
+    """``JacobiProlongation(ω)`` (``aggregation.jl:1-17``): ``P = T - (ω D^-1 A) T`` with LocalWeighting (the default),
+    D = row sums of |A| (``:26-47``), or DiagonalWeighting, D = diag(A) scaled by the spectral radius (``:19-24``)."""
 
     def __init__(self, omega):
         self.omega = omega
 
     def __call__(self, A, T, S=None, B=None, degree=1, weighting=None):
-        if weighting is not None and not isinstance(weighting, LocalWeighting):
-            raise NotImplementedError("only LocalWeighting (the reference's default) is implemented")
-        d_inv_s = _hostlib.local_weight(A, self.omega)
+        if isinstance(weighting, DiagonalWeighting):
+            d_inv_s = _diagonal_weight(A, self.omega)
+        elif weighting is None or isinstance(weighting, LocalWeighting):
+            d_inv_s = _hostlib.local_weight(A, self.omega)
+        else:
+            raise TypeError(f"unknown weighting {weighting!r}")
         P = T
         for _ in range(degree):
             P = _hostlib.sub(P, _hostlib.spgemm(d_inv_s, P))

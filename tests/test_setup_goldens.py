@@ -332,3 +332,38 @@ def test_host_galerkin_product_and_splitting_shortcuts(amg, fx):
         cp, rv = _hostlib.offdiag_pattern(t1)
         tt = s2.transpose()                      # s2 had its diagonal removed by RS
         assert np.array_equal(cp, tt.colptr) and np.array_equal(rv, tt.rowval)
+
+
+def test_approximate_spectral_radius_and_diagonal_weighting(amg):
+    """test/sa_tests.jl:270-312 (`test_approximate_spectral_radius`): the estimate equals max |eig| on small diagonal,
+    random and symmetrised matrices; and the `DiagonalWeighting` Jacobi prolongation smoother built on it
+    (aggregation.jl:19-24) scales D^-1 A by omega / rho."""
+    rng = np.random.default_rng(0)
+    cases = [np.array([[2.0, 0.0], [0.0, 1.0]]), np.array([[-2.0, 0.0], [0.0, 1.0]]),
+             np.array([[100.0, 0.0, 0.0], [0.0, 101.0, 0.0], [0.0, 0.0, 99.0]])]
+    cases += [rng.random((i, i)) for i in range(2, 6)]
+    for M in cases + [M + M.T for M in cases]:
+        expected = np.abs(np.linalg.eigvals(M)).max()
+        got = amg.approximate_spectral_radius(M, rng=np.random.default_rng(1))
+        assert np.isclose(got, expected, rtol=1e-8), (M.shape, got, expected)
+    # a sparse operator through the package's own matvec; a larger one within the stopping tolerance (1 %)
+    A = amg.poisson((12, 12))
+    rho = amg.approximate_spectral_radius(A, rng=np.random.default_rng(2))
+    exact = np.abs(np.linalg.eigvalsh(A.todense())).max()
+    assert abs(rho - exact) <= 0.02 * exact
+
+    # JacobiProlongation with DiagonalWeighting: P = T - (omega / rho(D^-1 A)) D^-1 A T
+    S, _ = amg.SymmetricStrength()(A)
+    T = amg.SparseMatrixCSC.from_dense(np.kron(np.eye(72), np.ones((2, 1))))
+    P = amg.JacobiProlongation(4.0 / 3.0)(A, T, S, None, 1, amg.DiagonalWeighting())
+    Ad = A.todense()
+    DinvA = Ad / np.diag(Ad)[:, None]
+    rho_exact = np.abs(np.linalg.eigvals(DinvA)).max()
+    Td = T.todense()
+    # P = T - c D^-1 A T with c = omega / rho: recover c from the result and compare with omega / rho(D^-1 A) (1 % estimate)
+    Y = DinvA @ Td
+    c = float(np.sum((Td - P.todense()) * Y) / np.sum(Y * Y))
+    assert np.abs(P.todense() - (Td - c * Y)).max() <= 1e-12
+    assert abs(c - (4.0 / 3.0) / rho_exact) <= 0.03 * c
+    ml = amg.smoothed_aggregation(A, smooth=lambda A_, T_, S_, B_: amg.JacobiProlongation(4.0 / 3.0)(A_, T_, S_, B_, 1, amg.DiagonalWeighting()))
+    assert len(ml) >= 2 and ml.levels[0].P.shape[0] == A.n
