@@ -18,6 +18,7 @@ from .gallery import elasticity_2d, elasticity_3d, poisson
 from .multilevel import (F, Level, MultiLevel, MultiLevelWorkspace, RugeStubenAMG, SmoothedAggregationAMG, V, W,
                          _solve, _solve_, grid_complexity, init, operator_complexity, solve, solve_)
 from .preconditioner import Preconditioner, aspreconditioner, backslash, cg, ldiv_, mul_
+from .precs import RugeStubenPreconBuilder, SmoothedAggregationPreconBuilder
 from .smoother import (SOR, BackwardSweep, ForwardSweep, GaussSeidel, Jacobi, SingularException, SymmetricSweep,
                        setup_smoother, smooth_)
 from .sparse import Adjoint, SparseMatrixCSC, adjoint, nnz, size

@@ -149,9 +149,14 @@ def test_preconditioned_cg_grids(amg):
         A = amg.poisson(sz)
         u0 = np.ones(A.n)
         b = A.matvec(u0)
-        for method in (amg.ruge_stuben, amg.smoothed_aggregation):
-            x = oracle.OracleHierarchy(method(A)).pcg(b, reltol=1e-10)
-            assert np.allclose(x, u0, rtol=1e-8, atol=0.0), (sz, method.__name__, np.abs(x - u0).max())
+        for builder in (amg.RugeStubenPreconBuilder(), amg.SmoothedAggregationPreconBuilder()):   # src/precs.jl
+            Pl, Pr = builder(A, None)
+            assert isinstance(Pl, amg.Preconditioner) and repr(Pr) == "I" and Pl.ml.levels[0].A is A
+            x = oracle.OracleHierarchy(Pl.ml).pcg(b, reltol=1e-10)
+            assert np.allclose(x, u0, rtol=1e-8, atol=0.0), (sz, type(builder).__name__, np.abs(x - u0).max())
+    # builder keywords reach the setup (precs.jl:12-17,31-36), the block size reaches the workspace
+    Pl, _ = amg.RugeStubenPreconBuilder(blocksize=2, max_levels=3)(amg.poisson((20, 20)), None)
+    assert len(Pl.ml) <= 3 and Pl.ml.workspace.bs == 2
 
 
 def test_regression_56(amg):
